@@ -1,0 +1,119 @@
+/* omniserve_b200 -- C ABI of the B200-native W4A8KV4 hot path.
+ *
+ * Drop-in boundary.  The reference (mit-han-lab/omniserve) has no C ABI: its boundary is 13 pybind11
+ * torch extensions under the python package `omniserve_backend` (kernels/setup.py:156-333) whose
+ * functions take torch::Tensor.  Every entry point below is what such an extension function does after it
+ * has unwrapped its tensors: raw device pointers, sizes, and the CUDA stream.  `INTEGRATION.md` shows
+ * the binding a maintainer of the reference would add for each; `omniserve_b200/backend/*.py` is that
+ * binding done with ctypes (same module / function names and argument order as the reference).
+ *
+ * Conventions: all pointers are device pointers unless stated; `stream` is a cudaStream_t passed as
+ * void*; every function is asynchronous w.r.t. the host and returns 0 or an OB_ERR_* code (reference:
+ * TORCH_CHECK -> RuntimeError; the ctypes mirror raises RuntimeError on non-zero).  fp16 = IEEE half.
+ * No torch types, no CPU fallback.
+ */
+#ifndef OMNISERVE_B200_H
+#define OMNISERVE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OB_OK 0
+#define OB_ERR_SHAPE 1
+#define OB_ERR_ALIGN 2
+#define OB_ERR_CUDA 3
+#define OB_ERR_DRIVER 4
+#define OB_ERR_ARG 5
+
+int ob_version(void);
+const char* ob_error_string(int code);
+
+/* ---- qgemm_w4a8_per_chn.gemm_forward_cuda   (kernels/csrc/qgemm/w4a8_per_chn/gemm_cuda.cu:601-657)
+ * out[M,N] = (in[M,K] . Wu4[N,K]^T) * wscales[n] * ascales[m] - w_szs[n] * a_ssums[m]
+ * kernel: int8 [N,K/2] in the reference tile layout (w4a8_linear.py:297-327); ldc = out row pitch (elements). */
+int ob_w4a8_gemm_per_chn(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales,
+                         const void* w_szs, const void* a_ssums, void* out_feats, int M, int N, int K, int ldc,
+                         void* stream);
+
+/* ---- qgemm_w4a8_per_group.gemm_forward_cuda (kernels/csrc/qgemm/w4a8_per_group/gemm_cuda.cu:635-707)
+ * w8 = q4*s2 + z2 (bytewise mod 256); out = (in . w8^T) * (wscales[n]*ascales[m]);  group = 128. */
+int ob_w4a8_gemm_per_group(const int8_t* in_feats, const int8_t* kernel, const int8_t* zeros,
+                           const int8_t* scales_i8, const void* wscales, const void* ascales, void* out_feats,
+                           int M, int N, int K, int ldc, void* stream);
+
+/* Same two GEMMs with scheduling knobs exposed for tests: force_bn in {0,16,32,64,128}, force_mode
+ * -1 auto / 0 data-parallel tiles / 1 stream-K, force_ctas 0 = all SMs. */
+int ob_w4a8_gemm_ex(int per_group, const int8_t* in_feats, const int8_t* kernel, const int8_t* zeros,
+                    const int8_t* scales_i8, const void* wscales, const void* ascales, const void* w_szs,
+                    const void* a_ssums, void* out_feats, int M, int N, int K, int ldc, int force_bn,
+                    int force_mode, int force_ctas, void* stream);
+
+/* ---- fused_kernels.invoke_quant / invoke_quant_fuse_sum (kernels/csrc/fused_kernels.cu:218-271), per-token */
+int ob_invoke_quant(int8_t* out, const void* input, void* scale, int num_tokens, int hidden, void* stream);
+int ob_invoke_quant_fuse_sum(int8_t* out, const void* input, void* input_sum, void* scale, int num_tokens,
+                             int hidden, void* stream);
+
+/* ---- layernorm_ops (kernels/csrc/layernorm_kernels.cu:409-513), per-token quant variants */
+int ob_rms_norm(void* out, const void* input, const void* weight, float eps, int num_tokens, int hidden,
+                void* stream);
+int ob_rms_norm_general(int8_t* out, const void* input, const void* weight, void* scaling, float eps,
+                        int num_tokens, int hidden, void* stream);
+int ob_rms_norm_general_fuse_sum(int8_t* out, const void* input, const void* weight, void* input_sum,
+                                 void* scaling, float eps, int num_tokens, int hidden, void* stream);
+
+/* ---- activation_ops.silu_and_mul (kernels/csrc/activation_kernels.cu:84-97); input [T,2d] -> out [T,d] */
+int ob_silu_and_mul(void* out, const void* input, int num_tokens, int d, void* stream);
+/* silu_and_mul fused with invoke_quant(_fuse_sum) (activation.py:54-77 runs them as two kernels);
+ * input_sum may be NULL. */
+int ob_silu_and_mul_quant(int8_t* out, const void* input, void* input_sum, void* scale, int num_tokens, int d,
+                          void* stream);
+/* fp16 elementwise add (llama_w4a8_unpad.py:425,437). n % 8 == 0. */
+int ob_add_f16(void* out, const void* a, const void* b, long long n, void* stream);
+
+/* ---- fused_attention_{pure_dense,fine_grained_dense,fine_grained_sparse}.single_query_attention
+ * (fused_attention_pure_dense/fused_attention.cpp:150-240; fine_grained/sparse_attention/fused_attention.cpp:198-377) */
+typedef struct ob_kv4_decode_args {
+  const void* q; const void* k; const void* v;       /* fp16 views [B,Hq,128] / [B,Hkv,128], head stride 128 */
+  long long q_batch_stride, k_batch_stride, v_batch_stride; /* elements */
+  void* out;                                          /* fp16 [B,Hq,128] contiguous */
+  const int64_t* retrieval_kv_pointers;               /* [B,2,r_max_pages] device addresses of K / V pages */
+  const int64_t* streaming_kv_pointers;               /* [B,2,s_max_pages] or NULL */
+  int r_max_pages, s_max_pages;
+  const int32_t* length_per_sample;                   /* [B] context length incl. the new token, or NULL */
+  const int32_t* retrieval_head_flags;                /* [Hkv] or NULL */
+  const int32_t* head_rank_table;                     /* [Hkv] or NULL */
+  const int32_t* dynamic_sparse_page_idxes;           /* [B,Hq,P] or NULL */
+  int num_dynamic_sparse_pages;
+  int batch, num_heads, num_kv_heads, head_dim, tokens_per_block;
+  int num_retrieval_kv_heads, num_streaming_kv_heads;
+  int sink_token_num, local_token_num, sink_block_num, local_block_num;
+  int timestep;                                       /* max cached tokens over the batch */
+  int rotary_embedding_dim; float rotary_base; float rotary_scale; /* scale = linear factor (1 = none) */
+  int force_split;                                    /* 0 = auto */
+} ob_kv4_decode_args;
+int ob_kv4_single_query_attention(const ob_kv4_decode_args* args, void* stream);
+
+/* ---- apply_bias_rope_update_kv_cache (fine_grained_common/update_kv_cache.cu:27-136), no bias */
+typedef struct ob_kv4_prefill_args {
+  void* qkv;                                          /* fp16 [T,(Hq+2Hkv)*128], RoPE applied in place to q,k */
+  const int32_t* seq_lens;                            /* [B] */
+  const int32_t* padding_offset;                      /* [T] */
+  int max_seq_len;
+  const int64_t* retrieval_kv_pointers; const int64_t* streaming_kv_pointers;
+  int r_max_pages, s_max_pages;
+  const int32_t* retrieval_head_flags; const int32_t* head_rank_table;
+  int num_tokens, batch, num_heads, num_kv_heads;
+  int num_retrieval_kv_heads, num_streaming_kv_heads;
+  int sink_token_num, local_token_num, sink_block_num, local_block_num;
+  int rotary_embedding_dim; float rotary_base; float rotary_scale;
+} ob_kv4_prefill_args;
+int ob_kv4_apply_rope_update_kv_cache(const ob_kv4_prefill_args* args, void* stream);
+
+/* ---- compute_padding_offsets (common/input_metadata_helper.cu:16-49) */
+int ob_compute_padding_offsets(int32_t* out, const int32_t* cu_seqlens, int batch, int max_seqlen, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

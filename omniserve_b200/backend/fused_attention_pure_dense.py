@@ -1,0 +1,26 @@
+"""omniserve_backend.fused_attention_pure_dense
+(reference: kernels/csrc/fused_attention/fused_attention_pure_dense/fused_attention.cpp:150-256)."""
+from . import _attn_common as A
+
+compute_padding_offsets = A.compute_padding_offsets
+
+
+def single_query_attention(q, k, v, kv_pointers, length_per_sample_, alibi_slopes_, memory_max_seqlen,
+                           tokens_per_block, size_per_token, timestep, rotary_embedding_dim, rotary_base,
+                           neox_rotary_style, int4_kv_cache, kv_cache_with_zeros):
+    """QServe dense decode attention over KV4 pages; appends the new token's K/V; returns fp16 [B,Hq,Dh]."""
+    A._require_kv4(int4_kv_cache, kv_cache_with_zeros)
+    if alibi_slopes_ is not None:
+        raise NotImplementedError("alibi is not used by the Llama path")
+    if not neox_rotary_style:
+        raise NotImplementedError("only NeoX-style rotary embedding (reference callers pass True)")
+    Hkv, Dh = k.shape[1], k.shape[-1]
+    if size_per_token != Hkv * Dh // 2:
+        raise RuntimeError("size_per_token must be num_kv_heads * head_dim / 2 for KV4")
+    return A.single_query(q, k, v, kv_pointers, None, None, None, None, length_per_sample_, tokens_per_block, Hkv, 0,
+                          0, 0, 0, 0, timestep, rotary_embedding_dim, rotary_base, 1.0)
+
+
+def apply_bias_rope_update_kv_cache(*args, **kwargs):
+    from .fused_attention_fine_grained_dense import apply_bias_rope_update_kv_cache as f
+    return f(*args, **kwargs)

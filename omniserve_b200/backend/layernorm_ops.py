@@ -1,0 +1,41 @@
+"""omniserve_backend.layernorm_ops (reference: kernels/csrc/layernorm.cpp:52-76, layernorm_kernels.cu:409-513)."""
+from .. import _lib as L
+
+
+def _rows(t):
+    h = t.shape[-1]
+    return t.numel() // h, h
+
+
+def rms_norm(out, input, weight, epsilon, use_quant=False):
+    if use_quant:
+        raise NotImplementedError("rms_norm(use_quant=True): static int8 path is not used by the W4A8 models")
+    L.require_cuda(out, input, weight)
+    T, H = _rows(input)
+    L.check(L.lib().ob_rms_norm(L.ptr(out), L.ptr(input), L.ptr(weight), float(epsilon), T, H, L.stream()), "rms_norm")
+
+
+def rms_norm_general(out, input, weight, scaling, epsilon, use_per_token_quant=False):
+    if not use_per_token_quant:
+        raise NotImplementedError("rms_norm_general: per-tensor scaling is not on the W4A8 path")
+    L.require_cuda(out, input, weight, scaling)
+    T, H = _rows(input)
+    L.check(
+        L.lib().ob_rms_norm_general(L.ptr(out), L.ptr(input), L.ptr(weight), L.ptr(scaling), float(epsilon), T, H,
+                                    L.stream()),
+        "rms_norm_general")
+
+
+def rms_norm_general_fuse_sum(out, input, weight, input_sum, scaling, epsilon, use_per_token_quant=False):
+    if not use_per_token_quant:
+        raise NotImplementedError("rms_norm_general_fuse_sum: per-tensor branch asserts false in the reference too")
+    L.require_cuda(out, input, weight, input_sum, scaling)
+    T, H = _rows(input)
+    L.check(
+        L.lib().ob_rms_norm_general_fuse_sum(L.ptr(out), L.ptr(input), L.ptr(weight), L.ptr(input_sum),
+                                             L.ptr(scaling), float(epsilon), T, H, L.stream()),
+        "rms_norm_general_fuse_sum")
+
+
+def invoke_dequant_add_residual_rms_norm_quant(*a, **k):
+    raise NotImplementedError("legacy W8A8 op, not on the W4A8KV4 path")

@@ -1,0 +1,363 @@
+// HBM-bound fused small ops around the W4A8 GEMMs: per-token INT8 activation quant (+sum),
+// "RMSNorm"+quant(+sum) with the reference's quirks, plain rms_norm, SiLU*mul (+ fused quant).
+//
+// Replaces: /root/reference/kernels/csrc/fused_kernels.cu:57-142, layernorm_kernels.cu:194-364,
+//           activation_kernels.cu:10-30.   One CTA per token row, 16-byte vector loads, the row is
+// kept in registers so HBM sees exactly one read of the input and one write of the output
+// (the reference re-reads the row 2-3x).  Fast-math intrinsics are used where the reference's
+// `--use_fast_math` build uses them so that the INT8 codes agree with the rebuilt reference.
+#include "ptx.cuh"
+#include "small_ops.h"
+
+namespace ob {
+
+constexpr int MAXV = 8;  // 16-byte vectors cached per thread
+
+OB_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+OB_DEVICE float warp_max(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+
+// Block-wide reduction of two values at once (op0 = sum or max, op1 = sum); result broadcast.
+template <bool MAX0>
+OB_DEVICE void block_reduce2(float& a, float& b, float* red /*[64]*/) {
+  a = MAX0 ? warp_max(a) : warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) { red[w] = a; red[32 + w] = b; }
+  __syncthreads();
+  float x = l < nw ? red[l] : (MAX0 ? -3.0e38f : 0.f);
+  float y = l < nw ? red[32 + l] : 0.f;
+  a = MAX0 ? warp_max(x) : warp_sum(x);
+  b = warp_sum(y);
+}
+
+union V8 {
+  uint4 u;
+  __half2 h2[4];
+  __half h[8];
+};
+
+OB_DEVICE uint2 pack8_i8(const float (&f)[8], float s) {
+  uint32_t b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (uint32_t)(uint8_t)f2i8_rni_sat(f[i] * s);
+  uint2 r;
+  r.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+  r.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// invoke_quant / invoke_quant_fuse_sum   (fused_kernels.cu:57-142)
+// ------------------------------------------------------------------------------------------------
+template <bool FUSE_SUM>
+__global__ void quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out, __half* __restrict__ scale,
+                             __half* __restrict__ sum, int H) {
+  __shared__ float red[64];
+  const size_t row = blockIdx.x;
+  const int nvec = H >> 3;
+  const uint4* src = reinterpret_cast<const uint4*>(in + row * H);
+  V8 v[MAXV];
+  float amax = 0.f, s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    if (idx < nvec) {
+      v[i].u = ld_nc_v4(src + idx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f = __half2float(v[i].h[j]);
+        s += f;
+        amax = fmaxf(amax, fabsf(f));
+      }
+    }
+  }
+  block_reduce2<true>(amax, s, red);
+  if (threadIdx.x == 0) {
+    scale[row] = __float2half_rn(__fdividef(amax, 127.0f));
+    if (FUSE_SUM) sum[row] = __float2half_rn(s);
+  }
+  const float qs = __fdividef(127.0f, amax);
+  uint2* dst = reinterpret_cast<uint2*>(out + row * H);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    if (idx < nvec) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __half2float(v[i].h[j]);
+      dst[idx] = pack8_i8(f, qs);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rms_norm_general(_fuse_sum)  (layernorm_kernels.cu:194-331): (x-mean)*rsqrt(mean(x^2)+eps)*gamma,
+// fp16-rounded before amax / sum, per-"reference thread" fp16 partial sums.  blockDim = refblock/8.
+// ------------------------------------------------------------------------------------------------
+template <bool FUSE_SUM>
+__global__ void rmsnorm_quant_kernel(const __half* __restrict__ in, const __half* __restrict__ gamma,
+                                     int8_t* __restrict__ out, __half* __restrict__ scale, __half* __restrict__ sum,
+                                     int H, float eps) {
+  __shared__ float red[64];
+  const size_t row = blockIdx.x;
+  const int nvec = H >> 3;
+  const uint4* src = reinterpret_cast<const uint4*>(in + row * H);
+  const uint4* gsrc = reinterpret_cast<const uint4*>(gamma);
+  V8 v[MAXV];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    if (idx < nvec) {
+      v[i].u = ld_nc_v4(src + idx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f = __half2float(v[i].h[j]);
+        s1 += f;
+        s2 += f * f;
+      }
+    }
+  }
+  block_reduce2<false>(s1, s2, red);
+  const float mean = __fdividef(s1, (float)H);
+  const float rstd = rsqrtf(__fdividef(s2, (float)H) + eps);
+  float amax = 1.013279e-06f;  // (half)1e-6f, layernorm_kernels.cu:279
+  __half hsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hsum[j] = __float2half_rn(0.f);
+  float nf[MAXV][8];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    if (idx < nvec) {
+      V8 g;
+      g.u = __ldg(gsrc + idx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f = ((__half2float(v[i].h[j]) - mean) * rstd) * __half2float(g.h[j]);
+        nf[i][j] = f;
+        const __half hv = __float2half_rn(f);
+        amax = fmaxf(amax, fabsf(__half2float(hv)));
+        if (FUSE_SUM) hsum[j] = __hadd(hsum[j], hv);
+      }
+    }
+  }
+  float ps = 0.f;
+  if (FUSE_SUM) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ps += __half2float(hsum[j]);
+  }
+  block_reduce2<true>(amax, ps, red);
+  if (threadIdx.x == 0) {
+    scale[row] = __float2half_rn(__fdividef(amax, 127.0f));
+    if (FUSE_SUM) sum[row] = __float2half_rn(ps);
+  }
+  const float qs = __fdividef(127.0f, amax);
+  uint2* dst = reinterpret_cast<uint2*>(out + row * H);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    if (idx < nvec) dst[idx] = pack8_i8(nf[i], qs);
+  }
+}
+
+// plain rms_norm, fp16 out (layernorm_kernels.cu:335-364): ((half)(x*rstd)) * w in half
+__global__ void rmsnorm_f16_kernel(const __half* __restrict__ in, const __half* __restrict__ gamma,
+                                   __half* __restrict__ out, int H, float eps) {
+  __shared__ float red[64];
+  const size_t row = blockIdx.x;
+  const int nvec = H >> 3;
+  const uint4* src = reinterpret_cast<const uint4*>(in + row * H);
+  const uint4* gsrc = reinterpret_cast<const uint4*>(gamma);
+  V8 v[MAXV];
+  float s2 = 0.f, dummy = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    if (idx < nvec) {
+      v[i].u = ld_nc_v4(src + idx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f = __half2float(v[i].h[j]);
+        s2 += f * f;
+      }
+    }
+  }
+  block_reduce2<false>(s2, dummy, red);
+  const float rstd = rsqrtf(__fdividef(s2, (float)H) + eps);
+  uint4* dst = reinterpret_cast<uint4*>(out + row * H);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    if (idx < nvec) {
+      V8 g, o;
+      g.u = __ldg(gsrc + idx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.h[j] = __hmul(__float2half_rn(__half2float(v[i].h[j]) * rstd), g.h[j]);
+      dst[idx] = o.u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// silu_and_mul (activation_kernels.cu:10-30) and the fused silu*mul -> per-token quant(+sum) that
+// removes the [T, inter] fp16 round trip of activation.py:54-64.
+// ------------------------------------------------------------------------------------------------
+OB_DEVICE __half silu_mul(__half g, __half u) {
+  const float x = __half2float(g);
+  const __half s = __float2half_rn(__fdividef(x, 1.0f + __expf(-x)));
+  return __hmul(s, u);
+}
+
+__global__ void silu_and_mul_kernel(const __half* __restrict__ in, __half* __restrict__ out, int d) {
+  const size_t row = blockIdx.x;
+  const uint4* g = reinterpret_cast<const uint4*>(in + row * 2 * d);
+  const uint4* u = reinterpret_cast<const uint4*>(in + row * 2 * d + d);
+  uint4* dst = reinterpret_cast<uint4*>(out + row * d);
+  for (int idx = threadIdx.x; idx < (d >> 3); idx += blockDim.x) {
+    V8 a, b, o;
+    a.u = ld_nc_v4(g + idx);
+    b.u = ld_nc_v4(u + idx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.h[j] = silu_mul(a.h[j], b.h[j]);
+    dst[idx] = o.u;
+  }
+}
+
+template <bool FUSE_SUM>
+__global__ void silu_mul_quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out,
+                                      __half* __restrict__ scale, __half* __restrict__ sum, int d) {
+  __shared__ float red[64];
+  const size_t row = blockIdx.x;
+  const int nvec = d >> 3;
+  const uint4* g = reinterpret_cast<const uint4*>(in + row * 2 * d);
+  const uint4* u = reinterpret_cast<const uint4*>(in + row * 2 * d + d);
+  V8 v[MAXV];
+  float amax = 0.f, s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    if (idx < nvec) {
+      V8 a, b;
+      a.u = ld_nc_v4(g + idx);
+      b.u = ld_nc_v4(u + idx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i].h[j] = silu_mul(a.h[j], b.h[j]);
+        const float f = __half2float(v[i].h[j]);
+        s += f;
+        amax = fmaxf(amax, fabsf(f));
+      }
+    }
+  }
+  block_reduce2<true>(amax, s, red);
+  if (threadIdx.x == 0) {
+    scale[row] = __float2half_rn(__fdividef(amax, 127.0f));
+    if (FUSE_SUM) sum[row] = __float2half_rn(s);
+  }
+  const float qs = __fdividef(127.0f, amax);
+  uint2* dst = reinterpret_cast<uint2*>(out + row * d);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    if (idx < nvec) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __half2float(v[i].h[j]);
+      dst[idx] = pack8_i8(f, qs);
+    }
+  }
+}
+
+// fp16 residual add (llama_w4a8_unpad.py:425,437 `residual + out_down_proj_act_buffer`)
+__global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out,
+                           size_t nvec) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    V8 x, y, o;
+    x.u = reinterpret_cast<const uint4*>(a)[i];
+    y.u = reinterpret_cast<const uint4*>(b)[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o.h2[j] = __hadd2(x.h2[j], y.h2[j]);
+    reinterpret_cast<uint4*>(out)[i] = o.u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+static int pick_threads(int nvec, int maxv) {
+  int t = (nvec + maxv - 1) / maxv;
+  t = ((t + 31) / 32) * 32;
+  if (t < 32) t = 32;
+  return t;
+}
+static int check(int H, int maxthreads = 1024) {
+  if (H <= 0 || (H & 7)) return OB_ERR_SHAPE;
+  if ((H >> 3) > MAXV * maxthreads) return OB_ERR_SHAPE;
+  return 0;
+}
+#define OB_LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? 0 : OB_ERR_CUDA)
+
+int quant_run(const __half* in, int8_t* out, __half* scale, __half* sum, int T, int H, cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (int e = check(H)) return e;
+  const int th = std::min(1024, pick_threads(H >> 3, 2));
+  if (sum) quant_kernel<true><<<T, th, 0, st>>>(in, out, scale, sum, H);
+  else quant_kernel<false><<<T, th, 0, st>>>(in, out, scale, nullptr, H);
+  return OB_LAUNCH_OK();
+}
+
+int rmsnorm_quant_run(const __half* in, const __half* gamma, int8_t* out, __half* scale, __half* sum, int T, int H,
+                      float eps, cudaStream_t st) {
+  if (T <= 0) return 0;
+  // reference block = min(H,1024) rounded up to 32 threads, one element per thread per iteration
+  int refblock = std::min(H, 1024);
+  refblock = 32 * ((refblock + 31) / 32);
+  if (int e = check(H, refblock / 8)) return e;
+  if (H % refblock != 0 && H > refblock) return OB_ERR_SHAPE;
+  const int th = std::max(32, refblock / 8);
+  if (sum) rmsnorm_quant_kernel<true><<<T, th, 0, st>>>(in, gamma, out, scale, sum, H, eps);
+  else rmsnorm_quant_kernel<false><<<T, th, 0, st>>>(in, gamma, out, scale, nullptr, H, eps);
+  return OB_LAUNCH_OK();
+}
+
+int rmsnorm_f16_run(const __half* in, const __half* gamma, __half* out, int T, int H, float eps, cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (int e = check(H)) return e;
+  rmsnorm_f16_kernel<<<T, std::min(1024, pick_threads(H >> 3, 2)), 0, st>>>(in, gamma, out, H, eps);
+  return OB_LAUNCH_OK();
+}
+
+int silu_and_mul_run(const __half* in, __half* out, int T, int d, cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (d <= 0 || (d & 7)) return OB_ERR_SHAPE;
+  silu_and_mul_kernel<<<T, std::min(1024, pick_threads(d >> 3, 2)), 0, st>>>(in, out, d);
+  return OB_LAUNCH_OK();
+}
+
+int silu_mul_quant_run(const __half* in, int8_t* out, __half* scale, __half* sum, int T, int d, cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (int e = check(d)) return e;
+  const int th = std::min(1024, pick_threads(d >> 3, 2));
+  if (sum) silu_mul_quant_kernel<true><<<T, th, 0, st>>>(in, out, scale, sum, d);
+  else silu_mul_quant_kernel<false><<<T, th, 0, st>>>(in, out, scale, nullptr, d);
+  return OB_LAUNCH_OK();
+}
+
+int add_run(const __half* a, const __half* b, __half* out, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (n & 7) return OB_ERR_SHAPE;
+  const size_t nvec = n >> 3;
+  const int blocks = (int)std::min<size_t>((nvec + 255) / 256, 148 * 8);
+  add_kernel<<<blocks, 256, 0, st>>>(a, b, out, nvec);
+  return OB_LAUNCH_OK();
+}
+
+}  // namespace ob

@@ -1,0 +1,18 @@
+#pragma once
+#include <algorithm>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "w4a8_gemm.h"  // error codes
+
+namespace ob {
+int quant_run(const __half* in, int8_t* out, __half* scale, __half* sum /*nullable*/, int T, int H, cudaStream_t st);
+int rmsnorm_quant_run(const __half* in, const __half* gamma, int8_t* out, __half* scale, __half* sum /*nullable*/,
+                      int T, int H, float eps, cudaStream_t st);
+int rmsnorm_f16_run(const __half* in, const __half* gamma, __half* out, int T, int H, float eps, cudaStream_t st);
+int silu_and_mul_run(const __half* in, __half* out, int T, int d, cudaStream_t st);
+int silu_mul_quant_run(const __half* in, int8_t* out, __half* scale, __half* sum /*nullable*/, int T, int d,
+                       cudaStream_t st);
+int add_run(const __half* a, const __half* b, __half* out, size_t n, cudaStream_t st);
+}  // namespace ob

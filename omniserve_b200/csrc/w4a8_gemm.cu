@@ -1,0 +1,556 @@
+// W4A8 GEMM for sm_100a: packed-INT4 weights -> INT8 in registers -> tensor memory (A operand) ->
+// tcgen05.mma kind::i8 with INT32 accumulators in TMEM; activations TMA-staged to 128B-swizzled shared
+// memory (B operand); QServe dequant fused in the epilogue.
+//
+// Replaces (same math, new design):
+//   per-channel: /root/reference/kernels/csrc/qgemm/w4a8_per_chn/gemm_cuda.cu:308-657
+//   per-group  : /root/reference/kernels/csrc/qgemm/w4a8_per_group/gemm_cuda.cu:333-707
+//
+// Orientation: C^T = W . X^T.  The 128 rows of a weight tile are the UMMA M dimension (TMEM lanes),
+// BN tokens are the UMMA N dimension (TMEM columns).  The reference's packed weight layout
+// [N/32][K/32][32 lanes][16 B] (w4a8_linear.py:297-327) is consumed *unchanged*: the 16 bytes a
+// "lane" owns are exactly the four registers of a `tcgen05.st.16x128b.x2` fragment
+// (rows c / c+8, K-bytes 4e.. / 16+4e..), low nibbles = rows n, high nibbles = rows n+16.
+//
+// Warp roles (384 threads): w0 = TMA/bulk producer, w1 = MMA issuer, w2 = TMEM allocator,
+// w4-7 = INT4->INT8 unpack (+ level-2 q*s2+z for per-group) into the TMEM A ring,
+// w8-11 = epilogue (TMEM -> regs -> fp32 math -> fp16 -> smem transpose -> 16 B global stores).
+//
+// Scheduling: persistent.  "DP" mode walks whole output tiles (prefill);  "SK" (stream-K) mode gives
+// every CTA an equal contiguous range of K-blocks so that small-M (decode) problems fill all SMs; tiles
+// that span CTAs are summed exactly in INT32 with cp.reduce.async.bulk (.add.s32) into an L2-resident
+// workspace and finished by the last contributor.
+#include "ptx.cuh"
+#include "w4a8_gemm.h"
+
+#include <algorithm>
+#include <mutex>
+#include <stdio.h>
+#include <unordered_map>
+
+namespace ob {
+
+constexpr int BM = 128;           // weight rows per tile  (UMMA M)
+constexpr int BK = 128;           // K bytes per pipeline stage (= one level-2 group)
+constexpr int W_STAGE = BM * BK / 2;  // 8192 packed bytes
+constexpr int NUM_THREADS = 384;
+constexpr int A_COLS_PER_STAGE = BK / 4;  // 32 TMEM columns hold 128 x 128 int8
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int B_STAGE = BN * BK;
+  static constexpr int S2_STAGE = 256;
+  static constexpr int ACC_BUFS = (BN >= 256) ? 1 : 2;
+  static constexpr int TMEM_A_BASE = ACC_BUFS * BN;  // columns
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int OUT_PITCH = BM + 8;            // halves
+  static constexpr int STAGING = (BN * OUT_PITCH * 2 > BN * BM * 4) ? BN * OUT_PITCH * 2 : BN * BM * 4;
+  static constexpr int SMEM_B = 0;
+  static constexpr int SMEM_W = SMEM_B + STAGES * B_STAGE;
+  static constexpr int SMEM_S2 = SMEM_W + STAGES * W_STAGE;
+  static constexpr int SMEM_STAGING = SMEM_S2 + STAGES * S2_STAGE;
+  static constexpr int SMEM_TOK = SMEM_STAGING + STAGING;      // float sa[BN], ss[BN]
+  static constexpr int SMEM_BAR = SMEM_TOK + BN * 8;
+  static constexpr int NUM_BARS = 3 * STAGES + 2 * ACC_BUFS;
+  static constexpr int SMEM_MISC = SMEM_BAR + NUM_BARS * 8;    // tmem slot, flags
+  static constexpr int SMEM_TOTAL = SMEM_MISC + 64 + 1024;      // + alignment slack
+  static_assert(TMEM_A_BASE + STAGES * A_COLS_PER_STAGE <= 512, "TMEM budget");
+  static_assert(SMEM_TOTAL <= 227 * 1024, "smem budget");
+};
+
+struct GemmParams {
+  const int8_t* qweight;    // [N/32][K/32][512]
+  const int8_t* s2_scales;  // per-group: [K/128][N] (N permuted in 32-blocks), else null
+  const int8_t* s2_zeros;
+  const __half* wscales;    // [N]
+  const __half* ascales;    // [M]
+  const __half* w_szs;      // per-channel: [N]
+  const __half* a_ssums;    // per-channel: [M]
+  __half* out;              // [M, ldc]
+  int32_t* ws;              // split-K workspace: [grid][BN*128] int32, zero between launches
+  int32_t* counters;        // [grid]
+  int M, N, K, ldc;
+  int n_tiles, m_tiles, kb_per_tile;
+  int mode;                 // 0 = DP, 1 = SK
+  int units_per_cta;        // SK: K-blocks per CTA
+  int group_m;              // DP raster: m-tiles per L2 group
+};
+
+struct Seg {
+  int tile, kb0, kb1;
+};
+
+struct SegIter {
+  int mode, KB, total_tiles, pos, end, tile, step;
+  OB_DEVICE void init(const GemmParams& p) {
+    mode = p.mode;
+    KB = p.kb_per_tile;
+    total_tiles = p.n_tiles * p.m_tiles;
+    if (mode == 0) {
+      tile = blockIdx.x;
+      step = gridDim.x;
+    } else {
+      long long tot = (long long)total_tiles * KB;
+      long long b = (long long)blockIdx.x * p.units_per_cta;
+      long long e = b + p.units_per_cta;
+      pos = (int)(b < tot ? b : tot);
+      end = (int)(e < tot ? e : tot);
+    }
+  }
+  OB_DEVICE bool next(Seg& s) {
+    if (mode == 0) {
+      if (tile >= total_tiles) return false;
+      s.tile = tile;
+      s.kb0 = 0;
+      s.kb1 = KB;
+      tile += step;
+      return true;
+    }
+    if (pos >= end) return false;
+    s.tile = pos / KB;
+    s.kb0 = pos - s.tile * KB;
+    int room = KB - s.kb0;
+    int left = end - pos;
+    s.kb1 = s.kb0 + (left < room ? left : room);
+    pos += s.kb1 - s.kb0;
+    return true;
+  }
+};
+
+OB_DEVICE void tile_coords(const GemmParams& p, int tile, int& nt, int& mt) {
+  if (p.mode == 0) {
+    int per_group = p.group_m * p.n_tiles;
+    int g = tile / per_group;
+    int r = tile - g * per_group;
+    int gm = min(p.group_m, p.m_tiles - g * p.group_m);
+    nt = r / gm;
+    mt = g * p.group_m + (r - nt * gm);
+  } else {
+    nt = tile / p.m_tiles;
+    mt = tile - nt * p.m_tiles;
+  }
+}
+
+// Bytewise (a + b) mod 256 on four packed bytes; `__vadd4` of the reference (per_group/gemm_cuda.cu:307).
+OB_DEVICE uint32_t vadd4(uint32_t a, uint32_t b) {
+  uint32_t s = (a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu);
+  return s ^ ((a ^ b) & 0x80808080u);
+}
+
+template <int BN, bool PER_GROUP>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem + C::SMEM_B;
+  uint8_t* sW = smem + C::SMEM_W;
+  uint8_t* sS2 = smem + C::SMEM_S2;
+  uint8_t* sStage = smem + C::SMEM_STAGING;
+  float* sTok = reinterpret_cast<float*>(smem + C::SMEM_TOK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SMEM_BAR);
+  uint64_t* full = bars;                       // TMA landed (B + packed W [+ s2])
+  uint64_t* empty = bars + C::STAGES;          // MMAs that read stage s finished
+  uint64_t* a_full = bars + 2 * C::STAGES;     // unpack warps filled the TMEM A slot
+  uint64_t* acc_full = bars + 3 * C::STAGES;
+  uint64_t* acc_empty = acc_full + C::ACC_BUFS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::SMEM_MISC);
+  int* sFlag = reinterpret_cast<int*>(smem + C::SMEM_MISC + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&act_map);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&a_full[i], 4);
+    }
+    for (int i = 0; i < C::ACC_BUFS; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int k32_per_row = p.K / 32;
+
+  if (warp == 0) {
+    // ================================================================ producer
+    if (lane == 0) {
+      SegIter it;
+      it.init(p);
+      Seg sg;
+      int stage = 0, phase = 0;
+      while (it.next(sg)) {
+        int nt, mt;
+        tile_coords(p, sg.tile, nt, mt);
+        const int n32_0 = nt * 4;
+        const int n32_cnt = min(4, p.N / 32 - n32_0);
+        const int n_cnt = n32_cnt * 32;
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint32_t tx = C::B_STAGE + n32_cnt * 2048 + (PER_GROUP ? 2 * n_cnt : 0);
+          mbar_arrive_expect_tx(&full[stage], tx);
+          tma_load_2d(sB + stage * C::B_STAGE, &act_map, kb * BK, mt * BN, &full[stage]);
+          const int8_t* wsrc = p.qweight + ((size_t)n32_0 * k32_per_row + (size_t)kb * 4) * 512;
+          for (int i = 0; i < n32_cnt; ++i)
+            bulk_g2s(sW + stage * W_STAGE + i * 2048, wsrc + (size_t)i * k32_per_row * 512, 2048, &full[stage]);
+          if (PER_GROUP) {
+            bulk_g2s(sS2 + stage * C::S2_STAGE, p.s2_scales + (size_t)kb * p.N + nt * BM, n_cnt, &full[stage]);
+            bulk_g2s(sS2 + stage * C::S2_STAGE + 128, p.s2_zeros + (size_t)kb * p.N + nt * BM, n_cnt, &full[stage]);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    SegIter it;
+    it.init(p);
+    Seg sg;
+    int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    constexpr uint32_t idesc = umma_idesc_i8(BM, BN, true, true);
+    while (it.next(sg)) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
+        mbar_wait(&a_full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sB + stage * C::B_STAGE));
+          const uint32_t a_tmem = tmem_base + C::TMEM_A_BASE + stage * A_COLS_PER_STAGE;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            umma_i8_ts(d_tmem, a_tmem + a * 8, bdesc + (uint64_t)(a * 2), idesc, (kb > sg.kb0 || a > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (kb == sg.kb1 - 1) umma_commit(&acc_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================================================================ INT4 -> INT8 unpack into TMEM
+    const int q = warp - 4;  // TMEM lane quarter == n32 block inside the tile
+    SegIter it;
+    it.init(p);
+    Seg sg;
+    int stage = 0, phase = 0;
+    while (it.next(sg)) {
+      for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t* wsm = sW + stage * W_STAGE + q * 2048 + lane * 16;
+        uint32_t sc[4], zr[4];
+        if (PER_GROUP) {
+          const uint32_t ps = *reinterpret_cast<const uint32_t*>(sS2 + stage * C::S2_STAGE + q * 32 + (lane >> 2) * 4);
+          const uint32_t pz = *reinterpret_cast<const uint32_t*>(sS2 + stage * C::S2_STAGE + 128 + q * 32 + (lane >> 2) * 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sc[j] = (ps >> (8 * j)) & 0xFFu;
+            zr[j] = ((pz >> (8 * j)) & 0xFFu) * 0x01010101u;
+          }
+        }
+        const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE + stage * A_COLS_PER_STAGE;
+        const uint32_t t_hi = t_lo + (16u << 16);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const uint4 v = *reinterpret_cast<const uint4*>(wsm + a * 512);
+          uint32_t l0 = v.x & 0x0F0F0F0Fu, l1 = v.y & 0x0F0F0F0Fu, l2 = v.z & 0x0F0F0F0Fu, l3 = v.w & 0x0F0F0F0Fu;
+          uint32_t h0 = (v.x >> 4) & 0x0F0F0F0Fu, h1 = (v.y >> 4) & 0x0F0F0F0Fu, h2 = (v.z >> 4) & 0x0F0F0F0Fu,
+                   h3 = (v.w >> 4) & 0x0F0F0F0Fu;
+          if (PER_GROUP) {
+            // rows: l0,l2 -> c (scale 0); l1,l3 -> c+8 (scale 1); h0,h2 -> c+16 (scale 2); h1,h3 -> c+24 (scale 3)
+            l0 = vadd4(l0 * sc[0], zr[0]); l2 = vadd4(l2 * sc[0], zr[0]);
+            l1 = vadd4(l1 * sc[1], zr[1]); l3 = vadd4(l3 * sc[1], zr[1]);
+            h0 = vadd4(h0 * sc[2], zr[2]); h2 = vadd4(h2 * sc[2], zr[2]);
+            h1 = vadd4(h1 * sc[3], zr[3]); h3 = vadd4(h3 * sc[3], zr[3]);
+          }
+          tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
+          tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[stage]);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================================================ epilogue
+    const int q = warp - 8;
+    const int et = threadIdx.x - 256;  // 0..127
+    SegIter it;
+    it.init(p);
+    Seg sg;
+    int acc = 0, acc_phase = 0;
+    __half* stage16 = reinterpret_cast<__half*>(sStage);
+    int32_t* stage32 = reinterpret_cast<int32_t*>(sStage);
+    while (it.next(sg)) {
+      int nt, mt;
+      tile_coords(p, sg.tile, nt, mt);
+      const int m0 = mt * BN;
+      const int n_row = nt * BM + q * 32 + lane;
+      const bool full_tile = (sg.kb0 == 0 && sg.kb1 == p.kb_per_tile);
+      const bool n_ok = n_row < p.N;
+      float wsc = 0.f, wsz = 0.f;
+      if (n_ok) {
+        wsc = __half2float(p.wscales[n_row]);
+        if (!PER_GROUP) wsz = __half2float(p.w_szs[n_row]);
+      }
+      // previous segment's staging users are done (barrier at the end of the loop body)
+      if (et < BN) {
+        const int m = m0 + et;
+        sTok[et] = (m < p.M) ? __half2float(p.ascales[m]) : 0.f;
+        sTok[BN + et] = (!PER_GROUP && m < p.M) ? __half2float(p.a_ssums[m]) : 0.f;
+      }
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // sTok visible
+      const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      if (full_tile) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_acc + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float ps = __int2float_rn((int)r[j]);
+            float o;
+            if (PER_GROUP) {
+              o = ps * (wsc * sTok[c0 + j]);
+            } else {
+              o = __fmaf_rn(-wsz, sTok[BN + c0 + j], (ps * wsc) * sTok[c0 + j]);
+            }
+            stage16[(c0 + j) * C::OUT_PITCH + q * 32 + lane] = __float2half_rn(o);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_acc + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) stage32[(c0 + j) * BM + q * 32 + lane] = (int)r[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+
+      if (full_tile) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // coalesced 16 B stores: 16 chunks of 8 halves per token row
+        const int chunk = et & 15;
+        const int n_base = nt * BM + chunk * 8;
+        if (n_base < p.N) {
+          for (int row = et >> 4; row < BN; row += 8) {
+            const int m = m0 + row;
+            if (m < p.M) {
+              const uint4 v = *reinterpret_cast<const uint4*>(stage16 + row * C::OUT_PITCH + chunk * 8);
+              *reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldc + n_base) = v;
+            }
+          }
+        }
+      } else {
+        // exact INT32 split-K: bulk reduce-add the partial tile into the L2 workspace slot of this tile
+        const int KB = p.kb_per_tile;
+        const int first_cta = (int)(((long long)sg.tile * KB) / p.units_per_cta);
+        const int last_cta = (int)(((long long)(sg.tile + 1) * KB - 1) / p.units_per_cta);
+        const int contributors = last_cta - first_cta + 1;
+        int32_t* slot = p.ws + (size_t)first_cta * (BN * BM);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          bulk_reduce_add_s32(slot, stage32, BN * BM * 4);
+          bulk_commit();
+          bulk_wait_all();
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          __threadfence();
+          const int old = atomicAdd(&p.counters[first_cta], 1);
+          *sFlag = (old == contributors - 1) ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*sFlag) {
+          __threadfence();
+          // finalize: elementwise over [BN tokens][128 n]; 8 consecutive n per item
+          for (int item = et; item < BN * 16; item += 128) {
+            const int row = item >> 4, chunk = item & 15;
+            const int m = m0 + row;
+            const int n_base = nt * BM + chunk * 8;
+            int4* src = reinterpret_cast<int4*>(slot + row * BM + chunk * 8);
+            int4 a0 = __ldcg(src), a1 = __ldcg(src + 1);
+            __stcg(src, make_int4(0, 0, 0, 0));
+            __stcg(src + 1, make_int4(0, 0, 0, 0));
+            if (m < p.M && n_base < p.N) {
+              const int av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              const float sa = sTok[row], ss = sTok[BN + row];
+              __align__(16) __half o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float w = __half2float(p.wscales[n_base + j]);
+                const float ps = __int2float_rn(av[j]);
+                float r;
+                if (PER_GROUP) r = ps * (w * sa);
+                else r = __fmaf_rn(-__half2float(p.w_szs[n_base + j]), ss, (ps * w) * sa);
+                o[j] = __float2half_rn(r);
+              }
+              *reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldc + n_base) = *reinterpret_cast<uint4*>(o);
+            }
+          }
+          if (et == 0) p.counters[first_cta] = 0;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // staging + sTok free for the next segment
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess) fn = (PFN_encodeTiled)f;
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int M, K, BN;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && M == o.M && K == o.K && BN == o.BN; }
+};
+struct MapHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (size_t)k.M * 1315423911u ^ (size_t)k.K * 2654435761u ^ (size_t)k.BN;
+  }
+};
+
+static int make_act_map(CUtensorMap* out, const void* ptr, int M, int K, int BN) {
+  static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  MapKey key{ptr, M, K, BN};
+  auto f = cache.find(key);
+  if (f != cache.end()) { *out = f->second; return 0; }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return OB_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)K};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return OB_ERR_DRIVER;
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int32_t* g_ws[16] = {nullptr};
+static int32_t* g_cnt[16] = {nullptr};
+constexpr size_t WS_INTS_PER_CTA = 128 * 128;  // BN(max 128 in SK mode) * BM
+
+static int ensure_workspace(int dev, int sms) {
+  if (g_ws[dev]) return 0;
+  size_t bytes = (size_t)sms * WS_INTS_PER_CTA * 4;
+  if (cudaMalloc(&g_ws[dev], bytes) != cudaSuccess) return OB_ERR_CUDA;
+  if (cudaMalloc(&g_cnt[dev], sms * 4) != cudaSuccess) return OB_ERR_CUDA;
+  cudaMemset(g_ws[dev], 0, bytes);
+  cudaMemset(g_cnt[dev], 0, sms * 4);
+  cudaDeviceSynchronize();
+  return 0;
+}
+
+template <int BN, bool PG>
+static int launch(const CUtensorMap& map, GemmParams& p, int grid, cudaStream_t st) {
+  using C = Cfg<BN>;
+  auto kern = w4a8_gemm_kernel<BN, PG>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL) != cudaSuccess)
+      return OB_ERR_CUDA;
+    attr_done = true;
+  }
+  kern<<<grid, NUM_THREADS, C::SMEM_TOTAL, st>>>(map, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : OB_ERR_CUDA;
+}
+
+int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
+  if (a.M <= 0) return 0;
+  if (a.N % 32 != 0 || a.K % 128 != 0 || a.ldc % 8 != 0) return OB_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(a.in_feats) & 15) || (reinterpret_cast<uintptr_t>(a.out_feats) & 15) ||
+      (reinterpret_cast<uintptr_t>(a.qweight) & 15))
+    return OB_ERR_ALIGN;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!g_num_sms) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = a.force_ctas > 0 ? std::min(a.force_ctas, g_num_sms) : g_num_sms;
+  if (int e = ensure_workspace(dev, g_num_sms)) return e;
+
+  int BN = a.M <= 16 ? 16 : a.M <= 32 ? 32 : a.M <= 64 ? 64 : 128;
+  if (a.force_bn > 0) BN = a.force_bn;
+  GemmParams p{};
+  p.qweight = a.qweight; p.s2_scales = a.s2_scales; p.s2_zeros = a.s2_zeros;
+  p.wscales = a.wscales; p.ascales = a.ascales; p.w_szs = a.w_szs; p.a_ssums = a.a_ssums;
+  p.out = a.out_feats; p.ws = g_ws[dev]; p.counters = g_cnt[dev];
+  p.M = a.M; p.N = a.N; p.K = a.K; p.ldc = a.ldc;
+  p.n_tiles = (a.N + BM - 1) / BM;
+  p.m_tiles = (a.M + BN - 1) / BN;
+  p.kb_per_tile = a.K / BK;
+  const long long tiles = (long long)p.n_tiles * p.m_tiles;
+  int grid;
+  const bool sk = a.force_mode >= 0 ? (a.force_mode == 1) : (tiles < 8LL * sms);
+  if (sk) {
+    p.mode = 1;
+    const long long total = tiles * p.kb_per_tile;
+    p.units_per_cta = (int)((total + sms - 1) / sms);
+    grid = (int)((total + p.units_per_cta - 1) / p.units_per_cta);
+  } else {
+    p.mode = 0;
+    p.group_m = std::max(1, 8192 / BN);  // 8192 tokens' activations stay L2-resident while all n-tiles sweep
+    p.units_per_cta = p.kb_per_tile;
+    grid = (int)std::min<long long>(tiles, sms);
+  }
+  CUtensorMap map;
+  if (int e = make_act_map(&map, a.in_feats, a.M, a.K, BN)) return e;
+#define OB_LAUNCH(bn)                                                              \
+  case bn:                                                                         \
+    return per_group ? launch<bn, true>(map, p, grid, st) : launch<bn, false>(map, p, grid, st);
+  switch (BN) {
+    OB_LAUNCH(16)
+    OB_LAUNCH(32)
+    OB_LAUNCH(64)
+    OB_LAUNCH(128)
+    default:
+      return OB_ERR_SHAPE;
+  }
+#undef OB_LAUNCH
+}
+
+}  // namespace ob
