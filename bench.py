@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the W4A8KV4 hot path on B200: Llama-3-8B decode at bs=64 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one decode iteration of the whole batch (64 sequences -> 64 new tokens) through the 32-layer
+W4A8KV4 stack: per layer rmsnorm+quant, qkv GEMM, KV4 attention (+append), quant, o_proj GEMM, add,
+rmsnorm+quant, gate_up GEMM, silu*mul+quant, down GEMM, add; then final norm, lm_head, argmax.
+The KV pages are filled beforehand by a real prefill of 64 x 1024 synthetic prompt tokens (reported separately
+as prefill tok/s and GEMM TOPS).  Context grows from 1024 during the run and wraps back to 1024 when the
+24-page budget (1536 tokens = in 1024 + out 512, README.md:281) is exhausted.
+
+Prints ONE JSON line (see the contract in the task description); `--impl reference` runs the same step through
+the reference's own kernels rebuilt for sm_100 (oracle/_ref), eagerly (the reference has no CUDA graphs and no TP).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PROMPT_LEN, GEN_LEN, BATCH = 1024, 512, 64
+PREFILL_SUB_BATCH = 8  # sequences per prefill chunk (8192 tokens), like the reference's chunked prefill
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev_index: int):
+        self.idx, self.proc, self.lines = dev_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def ref_loader():
+    import importlib.machinery
+    import importlib.util
+    d = os.path.join(ROOT, "oracle", "_ref", "omniserve_backend")
+
+    def load(name):
+        path = os.path.join(d, f"{name}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        loader = importlib.machinery.ExtensionFileLoader(name, path)
+        spec = importlib.util.spec_from_loader(name, loader)
+        m = importlib.util.module_from_spec(spec)
+        loader.exec_module(m)
+        return m
+    return load
+
+
+def cpu_baseline(cfg, seconds_budget: float = 20.0):
+    """torch-fp16 CPU path (oracle/cpu_path.py) for the same decode step on the host cores: ONE layer timed,
+    x32 extrapolated (bounded sample, stated in `sample`)."""
+    from oracle import cpu_path
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = dict(hidden=cfg.hidden_size, inter=cfg.intermediate_size, hq=cfg.num_attention_heads,
+             hkv=cfg.num_key_value_heads, dh=cfg.head_dim, eps=cfg.rms_norm_eps, base=cfg.rope_theta)
+    g = torch.Generator().manual_seed(0)
+    p = cpu_path.random_layer(c, g)
+    ctx = PROMPT_LEN + GEN_LEN // 2
+    kc = torch.randn(BATCH, c["hkv"], ctx + 8, c["dh"], generator=g).half()
+    vc = torch.randn(BATCH, c["hkv"], ctx + 8, c["dh"], generator=g).half()
+    x = torch.randn(BATCH, c["hidden"], generator=g).half()
+    lens = torch.full((BATCH,), ctx, dtype=torch.int64)
+    cpu_path.decode_layer(x, p, kc, vc, lens, c)  # warm-up
+    best, n, t_all = 1e9, 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t_all < seconds_budget and n < 20):
+        t0 = time.perf_counter()
+        cpu_path.decode_layer(x, p, kc, vc, lens, c)
+        best = min(best, time.perf_counter() - t0)
+        n += 1
+    step_s = best * cfg.num_hidden_layers
+    return {"value": BATCH / step_s, "unit": "tok/s", "cores": cores, "kind": "port",
+            "sample": f"1 decoder layer (bs={BATCH}, ctx={ctx}) best of {n}, x{cfg.num_hidden_layers} layers "
+                      f"extrapolated; lm_head/embedding excluded; torch CPU fp16 storage / fp32 math"}
+
+
+def time_kernels(model, graph_ctx: int):
+    """Per-kernel device time, measured live with CUDA events on the launching stream: each kernel class is
+    launched once per layer over the 32 layers' own weights / KV pools (>> L2, so every launch is HBM-cold)."""
+    cfg, b, B = model.cfg, model.buf, model.batch
+    ops = model.ops
+    res = {}
+
+    def timed(fn, reps=3):
+        best = 1e9
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best / cfg.num_hidden_layers  # ms per launch
+
+    qh, sc, sm = b.quantized_hidden_states_buffer[:B], b.quantized_scale_buffer[:B], b.quantized_sum_buffer[:B]
+    qh.random_(-127, 127); sc.fill_(0.02); sm.fill_(0.1)
+    b.quantized_attn_buffer[:B].random_(-127, 127); b.quantized_mlp_act_buffer[:B].random_(-127, 127)
+    gemm_bytes = {}
+    for name, x, out in (("qkv_proj", qh, b.qkv_proj_act_buffer[:B]), ("o_proj", b.quantized_attn_buffer[:B], b.out_down_proj_act_buffer[:B]),
+                         ("gate_up_proj", qh, b.gate_up_proj_act_buffer[:B]), ("down_proj", b.quantized_mlp_act_buffer[:B], b.out_down_proj_act_buffer[:B])):
+        def run(name=name, x=x, out=out):
+            for ly in model.layers:
+                ly[name](x, sc, sm, out)
+        res[name] = timed(run)
+        lin = model.layers[0][name]
+        gemm_bytes[name] = lin.qweight.numel() + B * lin.in_features + 2 * B * lin.out_features + 4 * lin.out_features + 4 * B
+    # attention at the bench's mid-run context
+    qkv = b.qkv_proj_act_buffer[:B]
+    qkv.normal_()
+    q3 = qkv[:, :model.q_size].view(B, model.hq, cfg.head_dim)
+    k3 = qkv[:, model.q_size:model.q_size + model.kv_size].view(B, model.hkv, cfg.head_dim)
+    v3 = qkv[:, model.q_size + model.kv_size:].view(B, model.hkv, cfg.head_dim)
+    lens = torch.full((B,), graph_ctx + 1, dtype=torch.int32, device=model.device)
+
+    def attn():
+        for li in range(cfg.num_hidden_layers):
+            ops.fused_attention_pure_dense.single_query_attention(q3, k3, v3, model.kv.tables[li], lens, None, model.max_ctx,
+                                                                  64, model.kv_size // 2, graph_ctx, cfg.head_dim,
+                                                                  cfg.rope_theta, True, True, True)
+    res["attention"] = timed(attn)
+    attn_bytes = B * graph_ctx * model.hkv * (128 + 8) + B * (2 * model.hq + 2 * model.hkv) * 128 * 2
+    return res, gemm_bytes, attn_bytes
+
+
+def prefill_gemm_tops(model, M=8192):
+    """Prefill-shaped W4A8 GEMMs (M = 8192-token chunk) timed with CUDA events -> achieved INT8 TOPS."""
+    dev = model.device
+    x = torch.randint(-127, 128, (M, max(model.cfg.hidden_size, model.inter)), dtype=torch.int8, device=dev)
+    sc = torch.full((M,), 0.02, dtype=torch.float16, device=dev)
+    sm = torch.full((M,), 0.1, dtype=torch.float16, device=dev)
+    out = {}
+    tot_ops = tot_ms = 0.0
+    for name in ("qkv_proj", "o_proj", "gate_up_proj", "down_proj"):
+        lin = model.layers[0][name]
+        xin = x[:, :lin.in_features].contiguous()
+        o = torch.empty((M, lin.out_features), dtype=torch.float16, device=dev)
+        for _ in range(2):
+            lin(xin, sc, sm, o)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 0
+        e0.record()
+        for ly in model.layers[:8]:
+            ly[name](xin, sc, sm, o)
+            n += 1
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        ops_ = 2.0 * M * lin.out_features * lin.in_features
+        out[name] = {"ms": ms, "tops": ops_ / ms / 1e9}
+        tot_ops += ops_; tot_ms += ms
+        del o
+    out["all"] = {"ms": tot_ms, "tops": tot_ops / tot_ms / 1e9}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (result is then marked invalid)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference" and rank != 0:
+        return 0  # the reference is single-GPU, single-process: rank 0 alone runs it
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    use_dist = world > 1 and a.impl == "ours"
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    tp = world if use_dist else 1
+
+    from omniserve_b200.model import DecodeGraph, LlamaConfig, LlamaW4A8, Ops, kernel_launches_per_decode_step
+    cfg = LlamaConfig.llama3_8b()
+    if a.layers:
+        cfg.num_hidden_layers = a.layers
+    hbm_peak, bf16_peak, peak_src = peaks()
+
+    if a.impl == "reference":
+        try:
+            ops = Ops(ref_loader())
+        except Exception as e:  # oracle/_ref not shipped
+            print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"}))
+            return 0
+        model = LlamaW4A8(cfg, dev, 0, 1, fuse_silu_quant=False, ops=ops)
+    else:
+        model = LlamaW4A8(cfg, dev, rank if use_dist else 0, tp)
+    max_ctx = PROMPT_LEN + GEN_LEN
+    model.alloc(BATCH, max_ctx, PREFILL_SUB_BATCH * PROMPT_LEN)
+
+    # ---------------------------------------------------------------- prefill (fills the KV4 pages)
+    g = torch.Generator().manual_seed(42)
+    prompts = torch.randint(0, cfg.vocab_size, (BATCH, PROMPT_LEN), generator=g)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    first = []
+    for s in range(0, BATCH, PREFILL_SUB_BATCH):
+        toks = prompts[s:s + PREFILL_SUB_BATCH].reshape(-1).to(dev)
+        first.append(model.prefill(toks, [PROMPT_LEN] * PREFILL_SUB_BATCH, seq_offset=s))
+    e1.record()
+    torch.cuda.synchronize()
+    prefill_ms = e0.elapsed_time(e1)
+    first = torch.cat(first)
+
+    # ---------------------------------------------------------------- decode
+    budget = GEN_LEN - 1  # steps until the page budget is exhausted
+    pinned_in = torch.zeros((BATCH,), dtype=torch.int64).pin_memory()
+    pinned_out = torch.zeros((BATCH,), dtype=torch.int64).pin_memory()
+    pinned_in.copy_(first.cpu())
+
+    if a.impl == "ours":
+        graph = DecodeGraph(model, max_ctx)
+        graph.tokens.copy_(first)
+
+        def step():
+            graph.graph.replay()
+
+        tokens_buf, out_buf = graph.tokens, graph.out
+    else:
+        model.prepare_decode()
+        tokens_buf = first.clone()
+        out_buf = torch.zeros_like(tokens_buf)
+
+        def step():
+            nxt = model.decode_step(tokens_buf, max_ctx)
+            out_buf.copy_(nxt)
+            tokens_buf.copy_(nxt)
+
+    state = {"done": 0}
+
+    def run_steps(n, e2e=False):
+        for _ in range(n):
+            if state["done"] >= budget:  # wrap the context back to the prompt length (pages are overwritten)
+                model.context_lens.fill_(PROMPT_LEN)
+                state["done"] = 0
+            if e2e:
+                tokens_buf.copy_(pinned_in, non_blocking=True)
+            step()
+            if e2e:
+                pinned_out.copy_(out_buf, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                pinned_in.copy_(pinned_out)
+            state["done"] += 1
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e=False):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        run_steps(n, e2e)
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if use_dist:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    run_steps(max(3, a.warmup))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx_start = PROMPT_LEN + state["done"]
+    ms = timed(a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    run_steps(3, e2e=True)
+    ms_e2e = timed(a.steps, e2e=True)
+
+    value = BATCH * a.steps / (ms / 1e3)
+    e2e_value = BATCH * a.steps / (ms_e2e / 1e3)
+
+    # ---------------------------------------------------------------- per-kernel roofline (rank 0 shapes)
+    mid_ctx = PROMPT_LEN + GEN_LEN // 2
+    kt, gemm_bytes, attn_bytes = time_kernels(model, mid_ctx)
+    gemm_ms = sum(kt[k] for k in gemm_bytes)
+    gemm_b = sum(gemm_bytes.values())
+    kernels = {
+        "w4a8_gemm(decode,4 launches/layer)": {"ms_per_layer": gemm_ms, "algorithmic_bytes": gemm_b,
+                                                "gbs": gemm_b / gemm_ms / 1e6, "frac_hbm": gemm_b / gemm_ms / 1e6 / hbm_peak,
+                                                "per_shape_ms": {k: kt[k] for k in gemm_bytes}},
+        "kv4_decode_attention": {"ms_per_layer": kt["attention"], "algorithmic_bytes": attn_bytes, "ctx": mid_ctx,
+                                 "gbs": attn_bytes / kt["attention"] / 1e6,
+                                 "frac_hbm": attn_bytes / kt["attention"] / 1e6 / hbm_peak},
+    }
+    dom = "w4a8_gemm(decode,4 launches/layer)" if gemm_ms >= kt["attention"] else "kv4_decode_attention"
+    roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+            "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+            "share_of_step": cfg.num_hidden_layers * kernels[dom]["ms_per_layer"] / (ms / a.steps)}
+    prefill = None
+    if a.impl == "ours" and tp == 1:
+        pg = prefill_gemm_tops(model)
+        prefill = {"tok_per_s": BATCH * PROMPT_LEN / (prefill_ms / 1e3), "ms": prefill_ms, "gemm_M8192": pg,
+                   "int8_peak_tops_provisional": 2 * bf16_peak,
+                   "gemm_frac_of_provisional_int8_peak": pg["all"]["tops"] / (2 * bf16_peak)}
+
+    if rank != 0:
+        return 0
+    line = {
+        "metric": "decode tok/s Llama-3-8B W4A8KV4 bs=64",
+        "value": value, "unit": "tok/s", "n_gpus": world if use_dist else 1, "steps": a.steps, "warmup": max(3, a.warmup),
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int8 (W4A8, s32 accumulate) + fp16 KV4 attention", "data": "synthetic (random-init weights, random prompts)",
+        "config": {"workload": "Llama-3-8B W4A8KV4 per-channel, qserve_benchmark.py semantics bs=64 in=1024 out=512: "
+                               "decode steps after a real 64x1024 prefill", "global_batch": BATCH, "prompt_len": PROMPT_LEN,
+                   "ctx_at_first_timed_step": ctx_start, "parallelism": f"tp{tp}", "cuda_graph": a.impl == "ours",
+                   "l2": "per-step working set (3.5 GB W4 weights + 2.8 GB KV4 + 1 GB lm_head) >> 126 MB L2; no flush needed",
+                   "layers": cfg.num_hidden_layers},
+        "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": BATCH * 8, "d2h_bytes_per_step": BATCH * 8,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": (kernel_launches_per_decode_step(cfg, model.fuse_silu_quant) * a.steps) if a.impl == "ours" else 0,
+        "clocks": clocks, "roofline": roof, "kernels": kernels, "prefill": prefill,
+        "step_floor_ms_at_measured_hbm": (model.weight_bytes() + model.lm_head.numel() * 2
+                                          + BATCH * mid_ctx * model.hkv * 136 * cfg.num_hidden_layers) / hbm_peak / 1e6,
+    }
+    if a.layers:
+        line["invalid"] = "debug run with fewer layers"
+    if a.impl == "reference":
+        line["impl"] = "reference"
+        line["config"]["note"] = ("reference = mit-han-lab/omniserve's own CUDA kernels (Ampere-era mma.sync / CUDA-core MMHA) "
+                                  "rebuilt for sm_100 by oracle/build_ref.py, same decoder-step sequencing, eager launches")
+    if not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(LlamaConfig.llama3_8b())
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

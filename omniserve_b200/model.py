@@ -21,8 +21,20 @@ from typing import List, Optional
 
 import torch
 
-from .backend import (activation_ops, fused_attention_fine_grained_dense, fused_attention_pure_dense, fused_kernels,
-                      layernorm_ops, qgemm_w4a8_per_chn, qgemm_w4a8_per_group)
+from . import backend as _backend_pkg  # noqa: F401  (the ctypes mirror of omniserve_backend)
+
+
+class Ops:
+    """The seven `omniserve_backend` modules the W4A8KV4 model code imports (llama_w4a8_unpad.py:32-37,
+    w4a8_linear.py:12-13, layernorm.py:16, activation.py:16, decoding_attention.py:5-10, ctx_update_kv.py:3-5).
+    Default: ours.  bench.py --impl reference passes the reference's own rebuilt modules instead."""
+
+    def __init__(self, loader=None):
+        import importlib
+        names = ("activation_ops", "fused_attention_fine_grained_dense", "fused_attention_pure_dense", "fused_kernels",
+                 "layernorm_ops", "qgemm_w4a8_per_chn", "qgemm_w4a8_per_group")
+        for n in names:
+            setattr(self, n, loader(n) if loader else importlib.import_module(f"omniserve_b200.backend.{n}"))
 
 TOKENS_PER_BLOCK = 64
 
@@ -60,8 +72,9 @@ class LlamaConfig:
 class W4A8Linear:
     """Buffers and forward of W4A8OF16LinearDynamicInputScale (w4a8_linear.py:16-139)."""
 
-    def __init__(self, in_features: int, out_features: int, group_size: int, device):
+    def __init__(self, in_features: int, out_features: int, group_size: int, device, ops: "Ops" = None):
         assert in_features % 128 == 0 and out_features % 32 == 0
+        self.ops = ops
         self.in_features, self.out_features, self.group_size = in_features, out_features, group_size
         self.per_channel = group_size == -1
         self.qweight = torch.zeros((out_features, in_features // 2), dtype=torch.int8, device=device)
@@ -96,10 +109,10 @@ class W4A8Linear:
 
     def __call__(self, x_i8, input_scales, input_sum, output_buffer):
         if self.per_channel:  # forward_per_chn (w4a8_linear.py:109-123)
-            qgemm_w4a8_per_chn.gemm_forward_cuda(x_i8, self.qweight, self.s1_scales, input_scales, self.s1_szeros,
+            self.ops.qgemm_w4a8_per_chn.gemm_forward_cuda(x_i8, self.qweight, self.s1_scales, input_scales, self.s1_szeros,
                                                  input_sum, output_buffer)
         else:  # forward_per_group (:125-139)
-            qgemm_w4a8_per_group.gemm_forward_cuda(x_i8, self.qweight, self.s2_zeros, self.s2_scales, self.s1_scales,
+            self.ops.qgemm_w4a8_per_group.gemm_forward_cuda(x_i8, self.qweight, self.s2_zeros, self.s2_scales, self.s1_scales,
                                                    input_scales, output_buffer)
 
 
@@ -150,7 +163,8 @@ class LlamaW4A8:
     """Llama decoder stack over the W4A8KV4 ops.  tp_rank / tp_size shard heads and MLP columns."""
 
     def __init__(self, cfg: LlamaConfig, device="cuda", tp_rank: int = 0, tp_size: int = 1, seed: int = 0,
-                 fuse_silu_quant: bool = True, process_group=None):
+                 fuse_silu_quant: bool = True, process_group=None, ops: Ops = None):
+        self.ops = ops or Ops()
         self.cfg, self.device, self.tp_rank, self.tp_size, self.pg = cfg, device, tp_rank, tp_size, process_group
         assert cfg.num_attention_heads % tp_size == 0 and cfg.num_key_value_heads % tp_size == 0
         assert cfg.intermediate_size % (tp_size * 128) == 0
@@ -167,10 +181,10 @@ class LlamaW4A8:
         self.layers = []
         for _ in range(cfg.num_hidden_layers):
             ly = {
-                "qkv_proj": W4A8Linear(H, self.q_size + 2 * self.kv_size, gs, device).random_init_(gen),
-                "o_proj": W4A8Linear(self.q_size, H, gs, device).random_init_(gen),
-                "gate_up_proj": W4A8Linear(H, 2 * self.inter, gs, device).random_init_(gen),
-                "down_proj": W4A8Linear(self.inter, H, gs, device).random_init_(gen),
+                "qkv_proj": W4A8Linear(H, self.q_size + 2 * self.kv_size, gs, device, self.ops).random_init_(gen),
+                "o_proj": W4A8Linear(self.q_size, H, gs, device, self.ops).random_init_(gen),
+                "gate_up_proj": W4A8Linear(H, 2 * self.inter, gs, device, self.ops).random_init_(gen),
+                "down_proj": W4A8Linear(self.inter, H, gs, device, self.ops).random_init_(gen),
                 "input_layernorm": (1.0 + 0.05 * torch.randn(H, generator=gen_rep)).half().to(device),
                 "post_attention_layernorm": (1.0 + 0.05 * torch.randn(H, generator=gen_rep)).half().to(device),
             }
@@ -184,6 +198,9 @@ class LlamaW4A8:
         self.lm_head = (torch.randn(self.vocab_local, H, generator=gen_v) * 0.02).half().to(device)
         self.kv: Optional[PagedKVCache] = None
         self.buf: Optional[ActivationBuffer] = None
+        # all heads are retrieval heads on the QServe dense path (ctx_attn_init.py:11-85)
+        self._flags = torch.ones(self.hkv, dtype=torch.int32, device=device)
+        self._rank = torch.arange(self.hkv, dtype=torch.int32, device=device)
 
     # ------------------------------------------------------------------ memory
     def weight_bytes(self) -> int:
@@ -207,6 +224,9 @@ class LlamaW4A8:
     # ------------------------------------------------------------------ one decoder layer
     def _layer(self, li: int, hidden, out_hidden, T: int, is_prompt: bool, meta):
         cfg, ly, b = self.cfg, self.layers[li], self.buf
+        layernorm_ops, fused_kernels, activation_ops = self.ops.layernorm_ops, self.ops.fused_kernels, self.ops.activation_ops
+        fused_attention_fine_grained_dense = self.ops.fused_attention_fine_grained_dense
+        fused_attention_pure_dense = self.ops.fused_attention_pure_dense
         qh = b.quantized_hidden_states_buffer[:T]
         sc, sm = b.quantized_scale_buffer[:T], b.quantized_sum_buffer[:T]
         qkv = b.qkv_proj_act_buffer[:T]
@@ -226,7 +246,7 @@ class LlamaW4A8:
             fused_attention_fine_grained_dense.apply_bias_rope_update_kv_cache(
                 qkv, meta["seq_lens"], None, meta["padding_offset"], self.kv.tables[li], None, meta["flags"],
                 meta["rank"], self.hq, self.hkv, meta["max_seq_len"], TOKENS_PER_BLOCK, self.kv_size // 2, 0, 0, 0, 0,
-                0, self.hkv, 0, cfg.head_dim, cfg.rope_theta, 1.0, 0, True, True, True)
+                0, self.hkv, 0, cfg.head_dim, cfg.rope_theta, 1.0, 8192, True, True, True)
             attn = meta["prefill_attn"](q3, k3, v3).reshape(T, self.q_size)
         else:
             # 3b. KV4 decode attention (decoding_attention.py:146-182)
@@ -280,7 +300,7 @@ class LlamaW4A8:
     def _sample(self, hidden_last):
         """final rms_norm + vocab-parallel lm_head + argmax (torch, as in the reference sampler)."""
         x = torch.empty_like(hidden_last)
-        layernorm_ops.rms_norm(x, hidden_last, self.norm_weight, self.cfg.rms_norm_eps)
+        self.ops.layernorm_ops.rms_norm(x, hidden_last, self.norm_weight, self.cfg.rms_norm_eps, False)
         logits = torch.matmul(x, self.lm_head.t())
         val, idx = logits.max(dim=-1)
         if self.tp_size == 1:
@@ -306,9 +326,9 @@ class LlamaW4A8:
         cu = torch.zeros(B + 1, dtype=torch.int32, device=dev)
         cu[1:] = torch.cumsum(sl, 0)
         max_len = max(seq_lens)
-        pad = fused_attention_fine_grained_dense.compute_padding_offsets(cu, max_len, T)
+        pad = self.ops.fused_attention_fine_grained_dense.compute_padding_offsets(cu, max_len, T)
         meta = {
-            "seq_lens": sl, "padding_offset": pad, "max_seq_len": max_len, "flags": None, "rank": None,
+            "seq_lens": sl, "padding_offset": pad, "max_seq_len": max_len, "flags": self._flags, "rank": self._rank,
             "prefill_attn": prefill_attention.make(cu, max_len, self.hq, self.hkv, self.cfg.head_dim),
         }
         if not self.fuse_silu_quant:
@@ -359,13 +379,15 @@ class DecodeGraph:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):  # allocates lazy workspaces, tensor maps, NCCL channels
-                self.out.copy_(model.decode_step(self.tokens, max_timestep))
+                self.out.copy_(model.decode_step(self.tokens.clone(), max_timestep))
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         model.context_lens.copy_(saved)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out.copy_(model.decode_step(self.tokens, max_timestep))
+            nxt = model.decode_step(self.tokens, max_timestep)
+            self.out.copy_(nxt)
+            self.tokens.copy_(nxt)  # the next replay consumes this step's samples without touching the host
         model.context_lens.copy_(saved)
         torch.cuda.synchronize()
 
