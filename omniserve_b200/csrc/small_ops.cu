@@ -59,7 +59,7 @@ OB_DEVICE uint2 pack8_i8(const float (&f)[8], float s) {
 // invoke_quant / invoke_quant_fuse_sum   (fused_kernels.cu:57-142)
 // ------------------------------------------------------------------------------------------------
 template <bool FUSE_SUM>
-__global__ void quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out, __half* __restrict__ scale,
+__global__ void __launch_bounds__(512) quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out, __half* __restrict__ scale,
                              __half* __restrict__ sum, int H) {
   __shared__ float red[64];
   const size_t row = blockIdx.x;
@@ -104,7 +104,7 @@ __global__ void quant_kernel(const __half* __restrict__ in, int8_t* __restrict__
 // fp16-rounded before amax / sum, per-"reference thread" fp16 partial sums.  blockDim = refblock/8.
 // ------------------------------------------------------------------------------------------------
 template <bool FUSE_SUM>
-__global__ void rmsnorm_quant_kernel(const __half* __restrict__ in, const __half* __restrict__ gamma,
+__global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __restrict__ in, const __half* __restrict__ gamma,
                                      int8_t* __restrict__ out, __half* __restrict__ scale, __half* __restrict__ sum,
                                      int H, float eps) {
   __shared__ float red[64];
@@ -171,7 +171,7 @@ __global__ void rmsnorm_quant_kernel(const __half* __restrict__ in, const __half
 }
 
 // plain rms_norm, fp16 out (layernorm_kernels.cu:335-364): ((half)(x*rstd)) * w in half
-__global__ void rmsnorm_f16_kernel(const __half* __restrict__ in, const __half* __restrict__ gamma,
+__global__ void __launch_bounds__(512) rmsnorm_f16_kernel(const __half* __restrict__ in, const __half* __restrict__ gamma,
                                    __half* __restrict__ out, int H, float eps) {
   __shared__ float red[64];
   const size_t row = blockIdx.x;
@@ -218,7 +218,7 @@ OB_DEVICE __half silu_mul(__half g, __half u) {
   return __hmul(s, u);
 }
 
-__global__ void silu_and_mul_kernel(const __half* __restrict__ in, __half* __restrict__ out, int d) {
+__global__ void __launch_bounds__(512) silu_and_mul_kernel(const __half* __restrict__ in, __half* __restrict__ out, int d) {
   const size_t row = blockIdx.x;
   const uint4* g = reinterpret_cast<const uint4*>(in + row * 2 * d);
   const uint4* u = reinterpret_cast<const uint4*>(in + row * 2 * d + d);
@@ -234,7 +234,7 @@ __global__ void silu_and_mul_kernel(const __half* __restrict__ in, __half* __res
 }
 
 template <bool FUSE_SUM>
-__global__ void silu_mul_quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out,
+__global__ void __launch_bounds__(512) silu_mul_quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out,
                                       __half* __restrict__ scale, __half* __restrict__ sum, int d) {
   __shared__ float red[64];
   const size_t row = blockIdx.x;
@@ -292,13 +292,18 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
 }
 
 // ---------------------------------------------------------------------------------------------- host
+// <= 512 threads per row (kernels are compiled with __launch_bounds__(512)); up to MAXV vectors per thread
 static int pick_threads(int nvec, int maxv) {
   int t = (nvec + maxv - 1) / maxv;
   t = ((t + 31) / 32) * 32;
+  if (t > 512) {
+    t = (nvec + MAXV - 1) / MAXV;
+    t = ((t + 31) / 32) * 32;
+  }
   if (t < 32) t = 32;
   return t;
 }
-static int check(int H, int maxthreads = 1024) {
+static int check(int H, int maxthreads = 512) {
   if (H <= 0 || (H & 7)) return OB_ERR_SHAPE;
   if ((H >> 3) > MAXV * maxthreads) return OB_ERR_SHAPE;
   return 0;
@@ -308,7 +313,7 @@ static int check(int H, int maxthreads = 1024) {
 int quant_run(const __half* in, int8_t* out, __half* scale, __half* sum, int T, int H, cudaStream_t st) {
   if (T <= 0) return 0;
   if (int e = check(H)) return e;
-  const int th = std::min(1024, pick_threads(H >> 3, 2));
+  const int th = pick_threads(H >> 3, 4);
   if (sum) quant_kernel<true><<<T, th, 0, st>>>(in, out, scale, sum, H);
   else quant_kernel<false><<<T, th, 0, st>>>(in, out, scale, nullptr, H);
   return OB_LAUNCH_OK();
@@ -331,21 +336,21 @@ int rmsnorm_quant_run(const __half* in, const __half* gamma, int8_t* out, __half
 int rmsnorm_f16_run(const __half* in, const __half* gamma, __half* out, int T, int H, float eps, cudaStream_t st) {
   if (T <= 0) return 0;
   if (int e = check(H)) return e;
-  rmsnorm_f16_kernel<<<T, std::min(1024, pick_threads(H >> 3, 2)), 0, st>>>(in, gamma, out, H, eps);
+  rmsnorm_f16_kernel<<<T, pick_threads(H >> 3, 4), 0, st>>>(in, gamma, out, H, eps);
   return OB_LAUNCH_OK();
 }
 
 int silu_and_mul_run(const __half* in, __half* out, int T, int d, cudaStream_t st) {
   if (T <= 0) return 0;
   if (d <= 0 || (d & 7)) return OB_ERR_SHAPE;
-  silu_and_mul_kernel<<<T, std::min(1024, pick_threads(d >> 3, 2)), 0, st>>>(in, out, d);
+  silu_and_mul_kernel<<<T, pick_threads(d >> 3, 4), 0, st>>>(in, out, d);
   return OB_LAUNCH_OK();
 }
 
 int silu_mul_quant_run(const __half* in, int8_t* out, __half* scale, __half* sum, int T, int d, cudaStream_t st) {
   if (T <= 0) return 0;
   if (int e = check(d)) return e;
-  const int th = std::min(1024, pick_threads(d >> 3, 2));
+  const int th = pick_threads(d >> 3, 4);
   if (sum) silu_mul_quant_kernel<true><<<T, th, 0, st>>>(in, out, scale, sum, d);
   else silu_mul_quant_kernel<false><<<T, th, 0, st>>>(in, out, scale, nullptr, d);
   return OB_LAUNCH_OK();
