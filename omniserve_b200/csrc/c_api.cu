@@ -55,33 +55,40 @@ int ob_w4a8_gemm_per_group(const int8_t* in_feats, const int8_t* kernel, const i
 }
 
 int ob_invoke_quant(int8_t* out, const void* input, void* scale, int T, int Hd, void* stream) {
+  if (T <= 0) return 0;
   if (!out || !input || !scale) return OB_ERR_ARG;
   return quant_run(H(input), out, HM(scale), nullptr, T, Hd, ST(stream));
 }
 int ob_invoke_quant_fuse_sum(int8_t* out, const void* input, void* input_sum, void* scale, int T, int Hd,
                              void* stream) {
+  if (T <= 0) return 0;
   if (!out || !input || !scale || !input_sum) return OB_ERR_ARG;
   return quant_run(H(input), out, HM(scale), HM(input_sum), T, Hd, ST(stream));
 }
 int ob_rms_norm(void* out, const void* input, const void* weight, float eps, int T, int Hd, void* stream) {
+  if (T <= 0) return 0;
   if (!out || !input || !weight) return OB_ERR_ARG;
   return rmsnorm_f16_run(H(input), H(weight), HM(out), T, Hd, eps, ST(stream));
 }
 int ob_rms_norm_general(int8_t* out, const void* input, const void* weight, void* scaling, float eps, int T, int Hd,
                         void* stream) {
+  if (T <= 0) return 0;
   if (!out || !input || !weight || !scaling) return OB_ERR_ARG;
   return rmsnorm_quant_run(H(input), H(weight), out, HM(scaling), nullptr, T, Hd, eps, ST(stream));
 }
 int ob_rms_norm_general_fuse_sum(int8_t* out, const void* input, const void* weight, void* input_sum, void* scaling,
                                  float eps, int T, int Hd, void* stream) {
+  if (T <= 0) return 0;
   if (!out || !input || !weight || !scaling || !input_sum) return OB_ERR_ARG;
   return rmsnorm_quant_run(H(input), H(weight), out, HM(scaling), HM(input_sum), T, Hd, eps, ST(stream));
 }
 int ob_silu_and_mul(void* out, const void* input, int T, int d, void* stream) {
+  if (T <= 0) return 0;
   if (!out || !input) return OB_ERR_ARG;
   return silu_and_mul_run(H(input), HM(out), T, d, ST(stream));
 }
 int ob_silu_and_mul_quant(int8_t* out, const void* input, void* input_sum, void* scale, int T, int d, void* stream) {
+  if (T <= 0) return 0;
   if (!out || !input || !scale) return OB_ERR_ARG;
   return silu_mul_quant_run(H(input), out, HM(scale), HM(input_sum), T, d, ST(stream));
 }

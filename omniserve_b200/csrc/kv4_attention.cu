@@ -120,25 +120,96 @@ struct AttnParams {
   int timestep;                                         // used when lengths == null
 };
 
-template <int G>
-__global__ void __launch_bounds__(ATT_THREADS)
-kv4_decode_kernel(const AttnParams p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  // layout: logits float [G][chunk_cap+1] | q_s half [G][128] | red float [...]
-  __shared__ __align__(16) __half q_s[G][DH];
+// ------------------------------------------------------------------------------------------------
+// Decode kernel.  160 threads: warps 0-3 compute, warp 4 = bulk-copy producer.
+//   * every visited (page, kv-head) slice -- 4 KB of K nibbles, 4 KB of V nibbles, 4 x 128 B of fp16
+//     scales / zeros -- is contiguous in the reference page layout, so the producer streams it into a
+//     4-stage shared-memory ring with cp.async.bulk + mbarrier (no per-thread global loads);
+//   * each compute warp owns 16 tokens of the page and runs flash-decoding on them with
+//     mma.sync.m16n8k16 (f16 x f16 -> f32):  S^T[16 tok x 8 heads] = (K nibbles - 8) . Q^T, online softmax,
+//     P^T moved into B-fragment form with movmatrix, O^T[128 dims x 8 heads] += (V nibbles - 8)^T . P'^T.
+//     The nibbles enter the MMAs as exact small integers; scale / zero are folded outside the MMAs (see
+//     header comment).  Token <-> MMA-row assignment kappa() is chosen so that both the K (LDS.128) and V
+//     (LDS.64) fragment loads are at most 2-way bank conflicted.
+//   * the four warps (and, for the split that owns it, the new token) are merged like KV splits.
+// ------------------------------------------------------------------------------------------------
+constexpr int V2_STAGES = 4;
+constexpr int V2_STAGE_BYTES = 2 * 4096 + 4 * 128;
+constexpr int V2_THREADS = 160;
+constexpr float LOG2E = 1.4426950408889634f;
+
+OB_DEVICE int kappa(int r) { return (r & 8) | ((r & 7) >> 1) | ((r & 1) << 2); }
+
+OB_DEVICE void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+OB_DEVICE uint32_t movmatrix_trans(uint32_t x) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(x));
+  return d;
+}
+OB_DEVICE uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+OB_DEVICE float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct Visit { int tab, lo, hi; };
+
+struct Visits {
+  int mode, n, tl;
+  int a1, b0, nA;       // streaming: range A = [0,a1), range B = [b0,tl); nA pages in A
+  int sink_blk, local_blk, dyn_pages;
+  const int* dyn;
+  OB_DEVICE void init(const SeqView& sv, int tl_, int dyn_pages_) {
+    mode = sv.mode; tl = tl_; dyn = sv.dyn; dyn_pages = dyn_pages_;
+    sink_blk = sv.sink_blk; local_blk = sv.local_blk;
+    if (mode == 0) n = (tl + TPB - 1) / TPB;
+    else if (mode == 2) n = tl > 0 ? dyn_pages : 0;
+    else {
+      a1 = min(sv.sink_tok, sv.n_valid);
+      b0 = sv.n_valid > sv.sink_tok ? sv.sink_tok + sv.gap : tl;
+      nA = (a1 + TPB - 1) / TPB;
+      const int nB = b0 < tl ? ((tl - 1) >> 6) - (b0 >> 6) + 1 : 0;
+      n = nA + nB;
+    }
+  }
+  OB_DEVICE Visit get(int v) const {
+    Visit r;
+    if (mode == 0) {
+      r.tab = v; r.lo = 0; r.hi = min(TPB, tl - v * TPB);
+    } else if (mode == 2) {
+      r.tab = dyn[v]; r.lo = 0; r.hi = (v == dyn_pages - 1) ? ((tl - 1) % TPB + 1) : TPB;
+    } else {
+      int x0, x1, blk;
+      if (v < nA) { x0 = 0; x1 = a1; blk = v; }
+      else { x0 = b0; x1 = tl; blk = (b0 >> 6) + (v - nA); }
+      r.lo = max(x0, blk * TPB) - blk * TPB;
+      r.hi = min(x1, blk * TPB + TPB) - blk * TPB;
+      r.tab = blk < sink_blk ? blk : sink_blk + (blk - sink_blk) % local_blk;
+    }
+    return r;
+  }
+};
+
+__global__ void __launch_bounds__(V2_THREADS)
+kv4_decode_kernel(const AttnParams p, const int G) {
+  extern __shared__ __align__(128) uint8_t ring[];  // V2_STAGES * V2_STAGE_BYTES, reused for the final merge
+  __shared__ __align__(16) __half q_s[8][DH];
   __shared__ __align__(16) __half kv_new[2][DH];
-  __shared__ float red[4][G][2];
-  __shared__ float qsum_s[G], cur_logit_s[G], stat_s[G][2];
-  __shared__ float o_red[4][G][DH];
+  __shared__ float qsum_s[8], cur_logit_s[8];
+  __shared__ float ml_s[4][8][2];
+  __shared__ __align__(8) uint64_t full[V2_STAGES], empty[V2_STAGES];
   __shared__ int flag_s;
-  float* logits = reinterpret_cast<float*>(smem_raw);
 
   const int split = blockIdx.x;
   const int b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = p.Hq / p.Hkv;
-  // G == group: one CTA per kv head; G == 1: one CTA per q head (dynamic page lists differ per q head)
-  const int hq0 = (G == 1) ? blockIdx.y : blockIdx.y * G;
+  const int hq0 = (G == 1 && group != 1) ? blockIdx.y : blockIdx.y * G;
   const int hkv = hq0 / group;
   const bool is_retrieval = p.retrieval_flags ? (p.retrieval_flags[hkv] != 0) : true;
   const int tl = (p.lengths ? p.lengths[b] : p.timestep + 1) - 1;  // cached tokens == position of the new one
@@ -155,8 +226,6 @@ kv4_decode_kernel(const AttnParams p) {
     if (p.dyn_idx) {
       sv.mode = 2;
       sv.dyn = p.dyn_idx + ((size_t)b * p.Hq + hq0) * p.dyn_pages;
-      sv.n_valid = (p.dyn_pages - 1) * TPB + (tl - 1) % TPB + 1;
-      if (tl <= 0) sv.n_valid = 0;
     }
     sv.gap = 0; sv.sink_tok = 0; sv.sink_blk = 0; sv.local_blk = 1;
   } else {
@@ -170,26 +239,31 @@ kv4_decode_kernel(const AttnParams p) {
     sv.sink_tok = p.sink_tok; sv.sink_blk = p.sink_blk; sv.local_blk = p.local_blk;
   }
   sv.data_bytes = sv.hpool * TPB * (DH / 2);
-
-  // this CTA's slice of the attended (logical) token list
-  const int per_split = ((sv.n_valid + p.n_split - 1) / p.n_split + 31) & ~31;
-  const int i0 = min(split * per_split, sv.n_valid);
-  const int i1 = min(i0 + per_split, sv.n_valid);
-  const int n_loc = i1 - i0;
+  Visits vis;
+  vis.init(sv, tl, p.dyn_pages);
+  const int per_split = (vis.n + p.n_split - 1) / p.n_split;
+  const int v0 = min(split * per_split, vis.n);
+  const int v1 = min(v0 + per_split, vis.n);
   const bool owns_current = (split == p.n_split - 1);
-  const int cap = per_split + 1;  // logits row pitch
 
+  if (tid == 0) {
+    for (int i = 0; i < V2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+    mbar_fence_init();
+  }
   // ------------------------------------------------------------------ prologue: q/k RoPE, append new K/V
   {
     const float pos = (float)tl;
-    // rotate q heads and k: thread d < 64 handles the NeoX pair (d, d + rot/2)
     const int half_rot = p.rotary_dim >> 1;
-    for (int item = tid; item < (G + 1) * (DH / 2); item += ATT_THREADS) {
+    for (int item = tid; item < 9 * (DH / 2); item += V2_THREADS) {
       const int h = item / (DH / 2), d = item - h * (DH / 2);
-      const __half* src = (h < G) ? p.q + (size_t)b * p.q_bs + (size_t)(hq0 + h) * DH
+      if (h < 8 && h >= G) {  // unused head rows of the 8-wide MMA N dimension
+        q_s[h][d] = __float2half_rn(0.f);
+        q_s[h][d + DH / 2] = __float2half_rn(0.f);
+        continue;
+      }
+      const __half* src = (h < 8) ? p.q + (size_t)b * p.q_bs + (size_t)(hq0 + h) * DH
                                   : p.k + (size_t)b * p.k_bs + (size_t)hkv * DH;
-      __half* dst = (h < G) ? q_s[h] : kv_new[0];
-      // generic mapping of the 64 "pair slots": rotary pairs first, then pass-through elements
+      __half* dst = (h < 8) ? q_s[h] : kv_new[0];
       if (d < half_rot) {
         const float inv_freq = (pos * p.rope_scale) / powf(p.rope_base, (float)(2 * d) / (float)p.rotary_dim);
         float sn, cs;
@@ -203,11 +277,11 @@ kv4_decode_kernel(const AttnParams p) {
         dst[e + 1] = src[e + 1];
       }
     }
-    for (int d = tid; d < DH; d += ATT_THREADS) kv_new[1][d] = p.v[(size_t)b * p.v_bs + (size_t)hkv * DH + d];
+    for (int d = tid; d < DH; d += V2_THREADS) kv_new[1][d] = p.v[(size_t)b * p.v_bs + (size_t)hkv * DH + d];
   }
   __syncthreads();
-  for (int h = warp; h < G; h += ATT_THREADS / 32) {
-    // qsum and the full-precision logit of the new token (Template.hpp:1356-1376)
+  for (int h = warp; h < 8; h += V2_THREADS / 32) {
+    // sum_d q_d and the full-precision logit of the new token (Template.hpp:1356-1376), log2 domain
     float s = 0.f, dot = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -220,14 +294,12 @@ kv4_decode_kernel(const AttnParams p) {
       s += __shfl_xor_sync(0xffffffffu, s, m);
       dot += __shfl_xor_sync(0xffffffffu, dot, m);
     }
-    if (lane == 0) { qsum_s[h] = s; cur_logit_s[h] = dot * 0.08838834764831845f; }
+    if (lane == 0) { qsum_s[h] = s; cur_logit_s[h] = dot * (0.08838834764831845f * LOG2E); }
   }
-  // append (only once per kv head: the split that owns the current token, first q head of the group)
-  const bool writer = owns_current && ((G > 1) || (hq0 == hkv * group));
-  if (writer && warp >= 2) {
+  const bool writer = owns_current && ((G > 1) || group == 1 || (hq0 == hkv * group));
+  if (writer && warp >= 2 && warp < 4) {
     const int which = warp - 2;  // 0 = K, 1 = V
     const int64_t* tab = which ? sv.vtab : sv.ktab;
-    // streaming heads write through the ring mapping, retrieval heads at the true page
     SeqView wv = sv;
     if (wv.mode == 2) wv.mode = 0;
     uint8_t* page = reinterpret_cast<uint8_t*>(tab[wv.tab_idx(tl)]);
@@ -240,248 +312,214 @@ kv4_decode_kernel(const AttnParams p) {
   }
   __syncthreads();
 
-  // ------------------------------------------------------------------ pass 1: logits = q.K^T
-  const float inv_sqrt = 0.08838834764831845f;  // 1/sqrt(128)
-  float lmax[G];
+  const float qk_scale = 0.08838834764831845f * LOG2E;  // 1/sqrt(128) * log2(e)
+  float acc[8][4];
+  float m0 = -1.0e30f, m1 = -1.0e30f, l0 = 0.f, l1 = 0.f, corr0 = 0.f, corr1 = 0.f;
 #pragma unroll
-  for (int h = 0; h < G; ++h) lmax[h] = -FLT_MAX;
-  {
-    const int c = tid & 3, ts = tid >> 2;
-    // q fragments in the nibble-pair order: pairs (8w+j, 8w+j+4) of this lane's 32 dims
-    __half2 qf[G][16];
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int h = 0; h < G; ++h)
-#pragma unroll
-      for (int w = 0; w < 4; ++w)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          qf[h][w * 4 + j] = __halves2half2(q_s[h][c * 32 + w * 8 + j], q_s[h][c * 32 + w * 8 + j + 4]);
-    float qs[G];
-#pragma unroll
-    for (int h = 0; h < G; ++h) qs[h] = qsum_s[h];
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 
-    for (int base = 0; base < n_loc; base += 32) {
-      const int li = base + ts;
-      const bool ok = li < n_loc;
-      const int pos = sv.pos_of(i0 + (ok ? li : 0));
-      const uint8_t* page = reinterpret_cast<const uint8_t*>(sv.ktab[sv.tab_idx(pos)]);
-      const int slot = pos & 63;
-      const uint4 kw = ld_nc_v4(page + (size_t)sv.rank * TPB * (DH / 2) + slot * (DH / 2) + c * 16);
-      const __half* scp = reinterpret_cast<const __half*>(page + sv.data_bytes) + sv.rank * TPB + slot;
-      const float ks = __half2float(scp[0]);
-      const float kz = __half2float(scp[sv.hpool * TPB]);
-      __half2 n2[16];
-      {
-        __half2 t[4];
-        nib8_to_h2(kw.x, t); n2[0] = t[0]; n2[1] = t[1]; n2[2] = t[2]; n2[3] = t[3];
-        nib8_to_h2(kw.y, t); n2[4] = t[0]; n2[5] = t[1]; n2[6] = t[2]; n2[7] = t[3];
-        nib8_to_h2(kw.z, t); n2[8] = t[0]; n2[9] = t[1]; n2[10] = t[2]; n2[11] = t[3];
-        nib8_to_h2(kw.w, t); n2[12] = t[0]; n2[13] = t[1]; n2[14] = t[2]; n2[15] = t[3];
+  if (warp == 4) {
+    // ================================================================ producer
+    if (lane == 0) {
+      int it = 0;
+      for (int v = v0; v < v1; ++v, ++it) {
+        const int s = it % V2_STAGES, ph = (it / V2_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const Visit vv = vis.get(v);
+        const uint8_t* kp = reinterpret_cast<const uint8_t*>(sv.ktab[vv.tab]);
+        const uint8_t* vp = reinterpret_cast<const uint8_t*>(sv.vtab[vv.tab]);
+        uint8_t* st = ring + s * V2_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], V2_STAGE_BYTES);
+        bulk_g2s(st, kp + (size_t)sv.rank * 4096, 4096, &full[s]);
+        bulk_g2s(st + 4096, vp + (size_t)sv.rank * 4096, 4096, &full[s]);
+        bulk_g2s(st + 8192, kp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
+        bulk_g2s(st + 8192 + 128, kp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
+        bulk_g2s(st + 8192 + 256, vp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
+        bulk_g2s(st + 8192 + 384, vp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
       }
+    }
+  } else {
+    // ================================================================ compute warps
+    const int g = lane >> 2, c = lane & 3;
+    uint32_t qB[16];
 #pragma unroll
-      for (int h = 0; h < G; ++h) {
-        __half2 a0 = __hmul2(qf[h][0], n2[0]), a1 = __hmul2(qf[h][8], n2[8]);
+    for (int w = 0; w < 4; ++w)
 #pragma unroll
-        for (int i = 1; i < 8; ++i) {
-          a0 = __hfma2(qf[h][i], n2[i], a0);
-          a1 = __hfma2(qf[h][8 + i], n2[8 + i], a1);
+      for (int j = 0; j < 4; ++j)
+        qB[w * 4 + j] = h2_as_u32(__halves2half2(q_s[g][c * 32 + w * 8 + j], q_s[g][c * 32 + w * 8 + j + 4]));
+    const float qs0 = qsum_s[2 * c], qs1 = qsum_s[2 * c + 1];
+    const int base = warp * 16;
+    const int tok_a = base + kappa(g), tok_b = base + kappa(g + 8);
+    const int vt0 = base + kappa(2 * c), vt1 = base + kappa(2 * c + 1), vt2 = base + kappa(8 + 2 * c),
+              vt3 = base + kappa(9 + 2 * c);
+    int it = 0;
+    for (int v = v0; v < v1; ++v, ++it) {
+      const int s = it % V2_STAGES, ph = (it / V2_STAGES) & 1;
+      const Visit vv = vis.get(v);
+      mbar_wait(&full[s], ph);
+      if (base < vv.hi && base + 16 > vv.lo) {
+        const uint8_t* st = ring + s * V2_STAGE_BYTES;
+        const __half* ksc = reinterpret_cast<const __half*>(st + 8192);
+        const __half* kzp = ksc + 64;
+        const __half* vsc = ksc + 128;
+        const __half* vzp = ksc + 192;
+        // ---------------- S^T = (K - 8) . Q^T
+        const uint4 ka = *reinterpret_cast<const uint4*>(st + tok_a * 64 + c * 16);
+        const uint4 kb = *reinterpret_cast<const uint4*>(st + tok_b * 64 + c * 16);
+        __half2 na[16], nb[16];
+        {
+          __half2 t[4];
+          nib8_to_h2(ka.x, t); na[0] = t[0]; na[1] = t[1]; na[2] = t[2]; na[3] = t[3];
+          nib8_to_h2(ka.y, t); na[4] = t[0]; na[5] = t[1]; na[6] = t[2]; na[7] = t[3];
+          nib8_to_h2(ka.z, t); na[8] = t[0]; na[9] = t[1]; na[10] = t[2]; na[11] = t[3];
+          nib8_to_h2(ka.w, t); na[12] = t[0]; na[13] = t[1]; na[14] = t[2]; na[15] = t[3];
+          nib8_to_h2(kb.x, t); nb[0] = t[0]; nb[1] = t[1]; nb[2] = t[2]; nb[3] = t[3];
+          nib8_to_h2(kb.y, t); nb[4] = t[0]; nb[5] = t[1]; nb[6] = t[2]; nb[7] = t[3];
+          nib8_to_h2(kb.z, t); nb[8] = t[0]; nb[9] = t[1]; nb[10] = t[2]; nb[11] = t[3];
+          nib8_to_h2(kb.w, t); nb[12] = t[0]; nb[13] = t[1]; nb[14] = t[2]; nb[15] = t[3];
         }
-        const float2 f0 = __half22float2(a0), f1 = __half22float2(a1);
-        float s = (f0.x + f0.y) + (f1.x + f1.y);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const float lg = (ks * s + ks * (8.0f - kz) * qs[h]) * inv_sqrt;
-        if (ok && c == 0) {
-          logits[h * cap + li] = lg;
-          lmax[h] = fmaxf(lmax[h], lg);
+        float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl)
+          mma16816(sacc, h2_as_u32(na[2 * sl]), h2_as_u32(nb[2 * sl]), h2_as_u32(na[2 * sl + 1]),
+                   h2_as_u32(nb[2 * sl + 1]), qB[2 * sl], qB[2 * sl + 1]);
+        const bool va = tok_a >= vv.lo && tok_a < vv.hi, vb = tok_b >= vv.lo && tok_b < vv.hi;
+        const float ksa = __half2float(ksc[tok_a]), kza = __half2float(kzp[tok_a]);
+        const float ksb = __half2float(ksc[tok_b]), kzb = __half2float(kzp[tok_b]);
+        const float la0 = va ? (ksa * sacc[0] + ksa * (8.f - kza) * qs0) * qk_scale : -INFINITY;
+        const float la1 = va ? (ksa * sacc[1] + ksa * (8.f - kza) * qs1) * qk_scale : -INFINITY;
+        const float lb0 = vb ? (ksb * sacc[2] + ksb * (8.f - kzb) * qs0) * qk_scale : -INFINITY;
+        const float lb1 = vb ? (ksb * sacc[3] + ksb * (8.f - kzb) * qs1) * qk_scale : -INFINITY;
+        // ---------------- online softmax over the 16 tokens (lanes with equal c share the heads 2c, 2c+1)
+        float x0 = fmaxf(la0, lb0), x1 = fmaxf(la1, lb1);
+#pragma unroll
+        for (int k = 4; k <= 16; k <<= 1) {
+          x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, k));
+          x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, k));
+        }
+        const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
+        if (__any_sync(0xffffffffu, n0 != m0 || n1 != m1)) {
+          const float f0 = ex2(m0 - n0), f1 = ex2(m1 - n1);
+          l0 *= f0; l1 *= f1; corr0 *= f0; corr1 *= f1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[j][0] *= f0; acc[j][1] *= f1; acc[j][2] *= f0; acc[j][3] *= f1; }
+          m0 = n0; m1 = n1;
+        }
+        const float pa0 = ex2(la0 - m0), pa1 = ex2(la1 - m1), pb0 = ex2(lb0 - m0), pb1 = ex2(lb1 - m1);
+        l0 += pa0 + pb0;
+        l1 += pa1 + pb1;
+        const float vsa = va ? __half2float(vsc[tok_a]) : 0.f, vza = va ? __half2float(vzp[tok_a]) : 8.f;
+        const float vsb = vb ? __half2float(vsc[tok_b]) : 0.f, vzb = vb ? __half2float(vzp[tok_b]) : 8.f;
+        const float qa0 = pa0 * vsa, qa1 = pa1 * vsa, qb0 = pb0 * vsb, qb1 = pb1 * vsb;
+        corr0 += qa0 * (vza - 8.f) + qb0 * (vzb - 8.f);
+        corr1 += qa1 * (vza - 8.f) + qb1 * (vzb - 8.f);
+        const uint32_t pb_lo = movmatrix_trans(h2_as_u32(__floats2half2_rn(qa0, qa1)));
+        const uint32_t pb_hi = movmatrix_trans(h2_as_u32(__floats2half2_rn(qb0, qb1)));
+        // ---------------- O^T += (V - 8)^T . P'^T
+        const uint2 w0 = *reinterpret_cast<const uint2*>(st + 4096 + vt0 * 64 + g * 8);
+        const uint2 w1 = *reinterpret_cast<const uint2*>(st + 4096 + vt1 * 64 + g * 8);
+        const uint2 w2 = *reinterpret_cast<const uint2*>(st + 4096 + vt2 * 64 + g * 8);
+        const uint2 w3 = *reinterpret_cast<const uint2*>(st + 4096 + vt3 * 64 + g * 8);
+        const __half2 c1032 = __halves2half2(__ushort_as_half(0x6408), __ushort_as_half(0x6408));
+        const __half2 c16th = __halves2half2(__ushort_as_half(0x2c00), __ushort_as_half(0x2c00));
+        const __half2 cm72 = __halves2half2(__ushort_as_half(0xd480), __ushort_as_half(0xd480));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t A = j < 4 ? w0.x : w0.y, B = j < 4 ? w1.x : w1.y, Cw = j < 4 ? w2.x : w2.y,
+                         D = j < 4 ? w3.x : w3.y;
+          const uint32_t sel = (uint32_t)(j & 3) | ((uint32_t)(4 + (j & 3)) << 8);
+          const uint32_t u01 = __byte_perm(A, B, sel), u23 = __byte_perm(Cw, D, sel);
+          uint32_t t0, t1, t2, t3;
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(t0) : "r"(u01));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(t1) : "r"(u01));
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(t2) : "r"(u23));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(t3) : "r"(u23));
+          const uint32_t a0 = h2_as_u32(__hsub2(*reinterpret_cast<__half2*>(&t0), c1032));
+          const uint32_t a1 = h2_as_u32(__hfma2(*reinterpret_cast<__half2*>(&t1), c16th, cm72));
+          const uint32_t a2 = h2_as_u32(__hsub2(*reinterpret_cast<__half2*>(&t2), c1032));
+          const uint32_t a3 = h2_as_u32(__hfma2(*reinterpret_cast<__half2*>(&t3), c16th, cm72));
+          mma16816(acc[j], a0, a1, a2, a3, pb_lo, pb_hi);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    // per-warp totals: l and corr are per-thread partials over the rows g of equal c
+#pragma unroll
+    for (int k = 4; k <= 16; k <<= 1) {
+      l0 += __shfl_xor_sync(0xffffffffu, l0, k);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, k);
+      corr0 += __shfl_xor_sync(0xffffffffu, corr0, k);
+      corr1 += __shfl_xor_sync(0xffffffffu, corr1, k);
     }
   }
-  // ------------------------------------------------------------------ softmax statistics
-  float lsum[G];
+  __syncthreads();  // every stage consumed: the ring can be reused as the merge buffer
+  float* obuf = reinterpret_cast<float*>(ring);  // [4 warps][8 heads][128 dims]
+  if (warp < 4) {
+    const int g = lane >> 2, c = lane & 3;
 #pragma unroll
-  for (int h = 0; h < G; ++h) {
-    float m = lmax[h];
-#pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
-    if (lane == 0) red[warp][h][0] = m;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int h = 0; h < G; ++h) {
-    float m = fmaxf(fmaxf(red[0][h][0], red[1][h][0]), fmaxf(red[2][h][0], red[3][h][0]));
-    if (owns_current) m = fmaxf(m, cur_logit_s[h]);
-    lmax[h] = m;
-    float s = 0.f;
-    for (int i = tid; i < n_loc; i += ATT_THREADS) {
-      const float e = __expf(logits[h * cap + i] - m);
-      logits[h * cap + i] = e;
-      s += e;
+    for (int j = 0; j < 8; ++j) {
+      // acc[j] = O^T[dims 16g+2j (rows g), 16g+2j+1 (rows g+8)][heads 2c, 2c+1]
+      float* o0 = obuf + ((warp * 8 + 2 * c) * DH) + 16 * g + 2 * j;
+      float* o1 = o0 + DH;
+      o0[0] = acc[j][0] - corr0; o0[1] = acc[j][2] - corr0;
+      o1[0] = acc[j][1] - corr1; o1[1] = acc[j][3] - corr1;
     }
-#pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
-    if (lane == 0) red[warp][h][1] = s;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int h = 0; h < G; ++h) {
-    float s = red[0][h][1] + red[1][h][1] + red[2][h][1] + red[3][h][1];
-    if (owns_current) s += __expf(cur_logit_s[h] - lmax[h]);
-    lsum[h] = s;
-  }
-  // n_split == 1: probabilities are normalised and rounded to fp16 before P.V like the reference (:1819-1831)
-  float pscale[G];
-#pragma unroll
-  for (int h = 0; h < G; ++h) pscale[h] = (p.n_split == 1) ? __fdividef(1.f, lsum[h] + 1.e-6f) : 1.f;
-
-  // ------------------------------------------------------------------ pass 2: out = P.V
-  float of[G][16];
-  float corr[G];
-#pragma unroll
-  for (int h = 0; h < G; ++h) {
-    corr[h] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) of[h][i] = 0.f;
-  }
-  {
-    const int c8 = tid & 7, ts = tid >> 3;
-    __half2 o2[G][8];
-#pragma unroll
-    for (int h = 0; h < G; ++h)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o2[h][i] = __float2half2_rn(0.f);
-    int since_flush = 0;
-    for (int base = 0; base < n_loc; base += 16) {
-      const int li = base + ts;
-      const bool ok = li < n_loc;
-      const int pos = sv.pos_of(i0 + (ok ? li : 0));
-      const uint8_t* page = reinterpret_cast<const uint8_t*>(sv.vtab[sv.tab_idx(pos)]);
-      const int slot = pos & 63;
-      const uint2 vw = ld_nc_v2(page + (size_t)sv.rank * TPB * (DH / 2) + slot * (DH / 2) + c8 * 8);
-      const __half* scp = reinterpret_cast<const __half*>(page + sv.data_bytes) + sv.rank * TPB + slot;
-      const float vs = ok ? __half2float(scp[0]) : 0.f;
-      const float vz = __half2float(scp[sv.hpool * TPB]);
-      __half2 n2[8];
-      {
-        __half2 t[4];
-        nib8_to_h2(vw.x, t); n2[0] = t[0]; n2[1] = t[1]; n2[2] = t[2]; n2[3] = t[3];
-        nib8_to_h2(vw.y, t); n2[4] = t[0]; n2[5] = t[1]; n2[6] = t[2]; n2[7] = t[3];
-      }
-#pragma unroll
-      for (int h = 0; h < G; ++h) {
-        float pr = ok ? logits[h * cap + li] * pscale[h] : 0.f;
-        pr = __half2float(__float2half_rn(pr));        // probabilities are fp16 in the reference
-        const float ps = pr * vs;
-        corr[h] += ps * (vz - 8.0f);
-        const __half2 p2 = __float2half2_rn(ps);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o2[h][i] = __hfma2(p2, n2[i], o2[h][i]);
-      }
-      if (++since_flush == 8) {
-        since_flush = 0;
-#pragma unroll
-        for (int h = 0; h < G; ++h)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 f = __half22float2(o2[h][i]);
-            of[h][2 * i] += f.x;
-            of[h][2 * i + 1] += f.y;
-            o2[h][i] = __float2half2_rn(0.f);
-          }
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < G; ++h)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 f = __half22float2(o2[h][i]);
-        of[h][2 * i] += f.x;
-        of[h][2 * i + 1] += f.y;
-      }
-    // reduce over the 4 token slots of this warp (lanes with equal c8), then over warps
-#pragma unroll
-    for (int h = 0; h < G; ++h) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x = of[h][i];
-        x += __shfl_xor_sync(0xffffffffu, x, 8);
-        x += __shfl_xor_sync(0xffffffffu, x, 16);
-        of[h][i] = x;
-      }
-      float cc = corr[h];
-      // corr is identical on the 8 lanes of a token slot; sum the 4 slots
-      cc += __shfl_xor_sync(0xffffffffu, cc, 8);
-      cc += __shfl_xor_sync(0xffffffffu, cc, 16);
-      corr[h] = cc;
-    }
-    if (lane < 8) {
-      // of[h][2*i + e] holds dim  c8*16 + (i/4)*8 + (i%4) + 4*e
-#pragma unroll
-      for (int h = 0; h < G; ++h)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int d = c8 * 16 + (i >> 2) * 8 + (i & 3);
-          o_red[warp][h][d] = of[h][2 * i] - corr[h];
-          o_red[warp][h][d + 4] = of[h][2 * i + 1] - corr[h];
-        }
+    if (g == 0) {
+      ml_s[warp][2 * c][0] = m0; ml_s[warp][2 * c][1] = l0;
+      ml_s[warp][2 * c + 1][0] = m1; ml_s[warp][2 * c + 1][1] = l1;
     }
   }
   __syncthreads();
-  // ------------------------------------------------------------------ finish / split merge
-  for (int item = tid; item < G * DH; item += ATT_THREADS) {
+  // ------------------------------------------------------------------ merge warps (+ new token), finish / split merge
+  const size_t slot = ((size_t)b * gridDim.y + blockIdx.y) * p.n_split + split;
+  for (int item = tid; item < G * DH; item += V2_THREADS) {
     const int h = item / DH, d = item - h * DH;
-    float o = o_red[0][h][d] + o_red[1][h][d] + o_red[2][h][d] + o_red[3][h][d];
-    o_red[0][h][d] = o;
-  }
-  if (tid < G) { stat_s[tid][0] = lmax[tid]; stat_s[tid][1] = lsum[tid]; }
-  __syncthreads();
-  if (p.n_split == 1) {
-    for (int item = tid; item < G * DH; item += ATT_THREADS) {
-      const int h = item / DH, d = item - h * DH;
-      const float inv = __fdividef(1.f, stat_s[h][1] + 1.e-6f);
-      float pc = __expf(cur_logit_s[h] - stat_s[h][0]) * inv;
-      pc = __half2float(__float2half_rn(pc));
-      const float o = o_red[0][h][d] + pc * __half2float(kv_new[1][d]);
-      p.out[((size_t)b * p.Hq + hq0 + h) * DH + d] = __float2half_rn(o);
+    float M = fmaxf(fmaxf(ml_s[0][h][0], ml_s[1][h][0]), fmaxf(ml_s[2][h][0], ml_s[3][h][0]));
+    if (owns_current) M = fmaxf(M, cur_logit_s[h]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float f = ex2(ml_s[w][h][0] - M);
+      num += f * obuf[(w * 8 + h) * DH + d];
+      den += f * ml_s[w][h][1];
     }
-    return;
-  }
-  // partials: unnormalised out (relative to local max), local max, local sum
-  {
-    const size_t slot = ((size_t)b * gridDim.y + blockIdx.y) * p.n_split + split;
-    for (int item = tid; item < G * DH; item += ATT_THREADS) {
-      const int h = item / DH, d = item - h * DH;
-      float o = o_red[0][h][d];
-      if (owns_current) o += __expf(cur_logit_s[h] - stat_s[h][0]) * __half2float(kv_new[1][d]);
-      p.part_o[(slot * G + h) * DH + d] = o;
+    if (owns_current) {
+      const float f = ex2(cur_logit_s[h] - M);
+      num += f * __half2float(kv_new[1][d]);
+      den += f;
     }
-    if (tid < G) {
-      p.part_ml[(slot * G + tid) * 2] = stat_s[tid][0];
-      p.part_ml[(slot * G + tid) * 2 + 1] = stat_s[tid][1];
-    }
-    __threadfence();
-    __syncthreads();
-    const int cidx = b * gridDim.y + blockIdx.y;
-    if (tid == 0) flag_s = (atomicAdd(&p.counters[cidx], 1) == p.n_split - 1);
-    __syncthreads();
-    if (!flag_s) return;
-    __threadfence();
-    const size_t slot0 = ((size_t)b * gridDim.y + blockIdx.y) * p.n_split;
-    for (int item = tid; item < G * DH; item += ATT_THREADS) {
-      const int h = item / DH, d = item - h * DH;
-      float gm = -FLT_MAX;
-      for (int s = 0; s < p.n_split; ++s) gm = fmaxf(gm, __ldcg(&p.part_ml[((slot0 + s) * G + h) * 2]));
-      float num = 0.f, den = 0.f;
-      for (int s = 0; s < p.n_split; ++s) {
-        const float w = __expf(__ldcg(&p.part_ml[((slot0 + s) * G + h) * 2]) - gm);
-        num += w * __ldcg(&p.part_o[((slot0 + s) * G + h) * DH + d]);
-        den += w * __ldcg(&p.part_ml[((slot0 + s) * G + h) * 2 + 1]);
-      }
+    if (p.n_split == 1) {
       p.out[((size_t)b * p.Hq + hq0 + h) * DH + d] = __float2half_rn(num * __fdividef(1.f, den + 1.e-6f));
+    } else {
+      p.part_o[(slot * 8 + h) * DH + d] = num;
+      if (d == 0) { p.part_ml[(slot * 8 + h) * 2] = M; p.part_ml[(slot * 8 + h) * 2 + 1] = den; }
     }
-    if (tid == 0) p.counters[cidx] = 0;
   }
+  if (p.n_split == 1) return;
+  __threadfence();
+  __syncthreads();
+  const int cidx = b * gridDim.y + blockIdx.y;
+  if (tid == 0) flag_s = (atomicAdd(&p.counters[cidx], 1) == p.n_split - 1);
+  __syncthreads();
+  if (!flag_s) return;
+  __threadfence();
+  const size_t slot0 = ((size_t)b * gridDim.y + blockIdx.y) * p.n_split;
+  for (int item = tid; item < G * DH; item += V2_THREADS) {
+    const int h = item / DH, d = item - h * DH;
+    float gm = -1.0e30f;
+    for (int s = 0; s < p.n_split; ++s) gm = fmaxf(gm, __ldcg(&p.part_ml[((slot0 + s) * 8 + h) * 2]));
+    float num = 0.f, den = 0.f;
+    for (int s = 0; s < p.n_split; ++s) {
+      const float w = ex2(__ldcg(&p.part_ml[((slot0 + s) * 8 + h) * 2]) - gm);
+      num += w * __ldcg(&p.part_o[((slot0 + s) * 8 + h) * DH + d]);
+      den += w * __ldcg(&p.part_ml[((slot0 + s) * 8 + h) * 2 + 1]);
+    }
+    p.out[((size_t)b * p.Hq + hq0 + h) * DH + d] = __float2half_rn(num * __fdividef(1.f, den + 1.e-6f));
+  }
+  if (tid == 0) p.counters[cidx] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -618,7 +656,7 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
   const int group = a.Hq / a.Hkv;
   const bool per_q = a.dyn_idx != nullptr;
   const int G = per_q ? 1 : group;
-  if (G != 1 && G != 2 && G != 4 && G != 8) return OB_ERR_SHAPE;
+  if (G < 1 || G > 8) return OB_ERR_SHAPE;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!g_att_sms) cudaDeviceGetAttribute(&g_att_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -636,43 +674,21 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
   p.rope_base = a.rotary_base; p.rope_scale = a.rotary_scale; p.rotary_dim = a.rotary_dim;
   p.timestep = a.timestep;
 
-  // upper bound of attended cached tokens (host knows only the max): timestep
-  const int max_ctx = std::max(1, a.max_attended);
+  // KV splits: enough CTAs to balance 148 SMs x ~4 resident CTAs, at least 4 pages per split
+  const int max_pages = std::max(1, (std::max(1, a.max_attended) + TPB - 1) / TPB);
   const int ctas_y = per_q ? a.Hq : a.Hkv;
-  int n_split = (max_ctx + MAX_CHUNK - 1) / MAX_CHUNK;
-  // fill the machine: aim for >= 2 CTAs per SM when the batch is small
   const int base_ctas = a.B * ctas_y;
-  while (base_ctas * n_split < 2 * g_att_sms && max_ctx / (n_split + 1) >= 256) ++n_split;
+  int n_split = 1;
+  while (base_ctas * n_split < 6 * g_att_sms && max_pages / (n_split + 1) >= 4 && n_split < 64) ++n_split;
   if (a.force_split > 0) n_split = a.force_split;
   p.n_split = n_split;
-  const int per_split = (((max_ctx + n_split - 1) / n_split) + 31) & ~31;
-  const size_t smem = (size_t)G * (per_split + 1) * 4;
-  if (smem > 160 * 1024) return OB_ERR_SHAPE;
   if (n_split > 1) {
     if (base_ctas > 65536) return OB_ERR_SHAPE;
-    if (int e = ensure_att_ws(dev, (size_t)base_ctas * n_split, G)) return e;
+    if (int e = ensure_att_ws(dev, (size_t)base_ctas * n_split, 8)) return e;
     p.part_o = g_part_o[dev]; p.part_ml = g_part_ml[dev]; p.counters = g_att_cnt[dev];
   }
   dim3 grid(n_split, ctas_y, a.B);
-#define OB_ATT(g)                                                                                         \
-  case g: {                                                                                               \
-    static size_t set = 0;                                                                                \
-    if (smem > 48 * 1024 && smem > set) {                                                                 \
-      if (cudaFuncSetAttribute(kv4_decode_kernel<g>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                               (int)smem) != cudaSuccess)                                                 \
-        return OB_ERR_CUDA;                                                                               \
-      set = smem;                                                                                         \
-    }                                                                                                     \
-    kv4_decode_kernel<g><<<grid, ATT_THREADS, smem, st>>>(p);                                             \
-    break;                                                                                                \
-  }
-  switch (G) {
-    OB_ATT(1)
-    OB_ATT(2)
-    OB_ATT(4)
-    OB_ATT(8)
-  }
-#undef OB_ATT
+  kv4_decode_kernel<<<grid, V2_THREADS, V2_STAGES * V2_STAGE_BYTES, st>>>(p, G);
   return cudaGetLastError() == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 

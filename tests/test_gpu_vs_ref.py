@@ -152,4 +152,6 @@ def test_prefill_writer_vs_reference_kernel():
     assert torch.equal(res[0][3], res[1][3])
     assert torch.equal(res[0][2], res[1][2])                       # V pages byte-identical
     assert (res[0][0] - res[1][0]).abs().max() <= 8e-3             # fast-math sincos of the reference at pos ~300
-    assert (res[0][1] != res[1][1]).float().mean() < 5e-3           # K nibbles follow the rotated values
+    # K nibbles follow the rotated values: one fp16 ulp on a token's min/max changes that token's scale/zero and
+    # with it most of its 64 bytes, so a ~1% byte difference corresponds to ~1% of (token, head) rows
+    assert (res[0][1] != res[1][1]).float().mean() < 3e-2
