@@ -62,6 +62,14 @@ int ob_rms_norm_general(int8_t* out, const void* input, const void* weight, void
 int ob_rms_norm_general_fuse_sum(int8_t* out, const void* input, const void* weight, void* input_sum,
                                  void* scaling, float eps, int num_tokens, int hidden, void* stream);
 
+/* Extensions (not in the reference): the fp16 residual add of llama_w4a8_unpad.py:425,437 fused into the norm
+ * that follows it.  x = hidden_in + delta (fp16); hidden_out = x; then as rms_norm_general(_fuse_sum) / rms_norm.
+ * input_sum may be NULL.  Bit-identical to torch.add followed by the unfused op. */
+int ob_add_rms_norm_general(int8_t* out, const void* hidden_in, const void* delta, void* hidden_out, const void* weight,
+                            void* input_sum, void* scaling, float eps, int num_tokens, int hidden, void* stream);
+int ob_add_rms_norm(void* out, const void* hidden_in, const void* delta, const void* weight, float eps, int num_tokens,
+                    int hidden, void* stream);
+
 /* ---- activation_ops.silu_and_mul (kernels/csrc/activation_kernels.cu:84-97); input [T,2d] -> out [T,d] */
 int ob_silu_and_mul(void* out, const void* input, int num_tokens, int d, void* stream);
 /* silu_and_mul fused with invoke_quant(_fuse_sum) (activation.py:54-77 runs them as two kernels);

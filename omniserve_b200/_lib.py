@@ -62,6 +62,8 @@ _SIGS = {
     "ob_rms_norm": ([c_p] * 3 + [c_f] + [c_i] * 2 + [c_p], c_i),
     "ob_rms_norm_general": ([c_p] * 4 + [c_f] + [c_i] * 2 + [c_p], c_i),
     "ob_rms_norm_general_fuse_sum": ([c_p] * 5 + [c_f] + [c_i] * 2 + [c_p], c_i),
+    "ob_add_rms_norm_general": ([c_p] * 7 + [c_f] + [c_i] * 2 + [c_p], c_i),
+    "ob_add_rms_norm": ([c_p] * 4 + [c_f] + [c_i] * 2 + [c_p], c_i),
     "ob_silu_and_mul": ([c_p] * 2 + [c_i] * 2 + [c_p], c_i),
     "ob_silu_and_mul_quant": ([c_p] * 4 + [c_i] * 2 + [c_p], c_i),
     "ob_add_f16": ([c_p] * 3 + [c_ll] + [c_p], c_i),

@@ -37,5 +37,24 @@ def rms_norm_general_fuse_sum(out, input, weight, input_sum, scaling, epsilon, u
         "rms_norm_general_fuse_sum")
 
 
+def add_rms_norm_general(out, hidden_in, delta, hidden_out, weight, input_sum, scaling, epsilon):
+    """Extension (not in the reference): hidden_out = hidden_in + delta (fp16, == torch.add), then
+    rms_norm_general(_fuse_sum)(out, hidden_out, ...) with per-token quant; input_sum may be None."""
+    L.require_cuda(out, hidden_in, delta, hidden_out, weight, input_sum, scaling)
+    T, H = _rows(hidden_in)
+    L.check(
+        L.lib().ob_add_rms_norm_general(L.ptr(out), L.ptr(hidden_in), L.ptr(delta), L.ptr(hidden_out), L.ptr(weight),
+                                        L.ptr(input_sum), L.ptr(scaling), float(epsilon), T, H, L.stream()),
+        "add_rms_norm_general")
+
+
+def add_rms_norm(out, hidden_in, delta, weight, epsilon):
+    """Extension: rms_norm(out, hidden_in + delta, weight, eps) with the add fused (fp16 out)."""
+    L.require_cuda(out, hidden_in, delta, weight)
+    T, H = _rows(hidden_in)
+    L.check(L.lib().ob_add_rms_norm(L.ptr(out), L.ptr(hidden_in), L.ptr(delta), L.ptr(weight), float(epsilon), T, H,
+                                    L.stream()), "add_rms_norm")
+
+
 def invoke_dequant_add_residual_rms_norm_quant(*a, **k):
     raise NotImplementedError("legacy W8A8 op, not on the W4A8KV4 path")

@@ -68,19 +68,32 @@ int ob_invoke_quant_fuse_sum(int8_t* out, const void* input, void* input_sum, vo
 int ob_rms_norm(void* out, const void* input, const void* weight, float eps, int T, int Hd, void* stream) {
   if (T <= 0) return 0;
   if (!out || !input || !weight) return OB_ERR_ARG;
-  return rmsnorm_f16_run(H(input), H(weight), HM(out), T, Hd, eps, ST(stream));
+  return rmsnorm_f16_run(H(input), nullptr, H(weight), HM(out), T, Hd, eps, ST(stream));
 }
 int ob_rms_norm_general(int8_t* out, const void* input, const void* weight, void* scaling, float eps, int T, int Hd,
                         void* stream) {
   if (T <= 0) return 0;
   if (!out || !input || !weight || !scaling) return OB_ERR_ARG;
-  return rmsnorm_quant_run(H(input), H(weight), out, HM(scaling), nullptr, T, Hd, eps, ST(stream));
+  return rmsnorm_quant_run(H(input), nullptr, nullptr, H(weight), out, HM(scaling), nullptr, T, Hd, eps, ST(stream));
 }
 int ob_rms_norm_general_fuse_sum(int8_t* out, const void* input, const void* weight, void* input_sum, void* scaling,
                                  float eps, int T, int Hd, void* stream) {
   if (T <= 0) return 0;
   if (!out || !input || !weight || !scaling || !input_sum) return OB_ERR_ARG;
-  return rmsnorm_quant_run(H(input), H(weight), out, HM(scaling), HM(input_sum), T, Hd, eps, ST(stream));
+  return rmsnorm_quant_run(H(input), nullptr, nullptr, H(weight), out, HM(scaling), HM(input_sum), T, Hd, eps, ST(stream));
+}
+int ob_add_rms_norm_general(int8_t* out, const void* hidden_in, const void* delta, void* hidden_out, const void* weight,
+                            void* input_sum, void* scaling, float eps, int T, int Hd, void* stream) {
+  if (T <= 0) return 0;
+  if (!out || !hidden_in || !delta || !hidden_out || !weight || !scaling) return OB_ERR_ARG;
+  return rmsnorm_quant_run(H(hidden_in), H(delta), HM(hidden_out), H(weight), out, HM(scaling), HM(input_sum), T, Hd, eps,
+                           ST(stream));
+}
+int ob_add_rms_norm(void* out, const void* hidden_in, const void* delta, const void* weight, float eps, int T, int Hd,
+                    void* stream) {
+  if (T <= 0) return 0;
+  if (!out || !hidden_in || !delta || !weight) return OB_ERR_ARG;
+  return rmsnorm_f16_run(H(hidden_in), H(delta), H(weight), HM(out), T, Hd, eps, ST(stream));
 }
 int ob_silu_and_mul(void* out, const void* input, int T, int d, void* stream) {
   if (T <= 0) return 0;

@@ -20,6 +20,7 @@
 // Numerics therefore agree with the reference to ~1e-3 (north-star tolerance), not bit-exactly; the KV
 // page bytes written for the new token follow the reference formula exactly.
 #include "kv4_attention.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -195,16 +196,17 @@ struct Visits {
   }
 };
 
-__global__ void __launch_bounds__(V2_THREADS)
+__global__ void __launch_bounds__(V2_THREADS, 4)
 kv4_decode_kernel(const AttnParams p, const int G) {
   extern __shared__ __align__(128) uint8_t ring[];  // V2_STAGES * V2_STAGE_BYTES, reused for the final merge
   __shared__ __align__(16) __half q_s[8][DH];
   __shared__ __align__(16) __half kv_new[2][DH];
-  __shared__ float qsum_s[8], cur_logit_s[8];
+  __shared__ float qsum_s[8], qbias_s[8], cur_logit_s[8];
   __shared__ float ml_s[4][8][2];
   __shared__ __align__(8) uint64_t full[V2_STAGES], empty[V2_STAGES];
   __shared__ int flag_s;
 
+  pdl_trigger();
   const int split = blockIdx.x;
   const int b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -250,82 +252,25 @@ kv4_decode_kernel(const AttnParams p, const int G) {
     for (int i = 0; i < V2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
     mbar_fence_init();
   }
-  // ------------------------------------------------------------------ prologue: q/k RoPE, append new K/V
-  {
-    const float pos = (float)tl;
-    const int half_rot = p.rotary_dim >> 1;
-    for (int item = tid; item < 9 * (DH / 2); item += V2_THREADS) {
-      const int h = item / (DH / 2), d = item - h * (DH / 2);
-      if (h < 8 && h >= G) {  // unused head rows of the 8-wide MMA N dimension
-        q_s[h][d] = __float2half_rn(0.f);
-        q_s[h][d + DH / 2] = __float2half_rn(0.f);
-        continue;
-      }
-      const __half* src = (h < 8) ? p.q + (size_t)b * p.q_bs + (size_t)(hq0 + h) * DH
-                                  : p.k + (size_t)b * p.k_bs + (size_t)hkv * DH;
-      __half* dst = (h < 8) ? q_s[h] : kv_new[0];
-      if (d < half_rot) {
-        const float inv_freq = (pos * p.rope_scale) / powf(p.rope_base, (float)(2 * d) / (float)p.rotary_dim);
-        float sn, cs;
-        sincosf(inv_freq, &sn, &cs);
-        const float x = __half2float(src[d]), y = __half2float(src[d + half_rot]);
-        dst[d] = __float2half_rn(cs * x - sn * y);
-        dst[d + half_rot] = __float2half_rn(cs * y + sn * x);
-      } else {
-        const int e = p.rotary_dim + 2 * (d - half_rot);
-        dst[e] = src[e];
-        dst[e + 1] = src[e + 1];
-      }
-    }
-    for (int d = tid; d < DH; d += V2_THREADS) kv_new[1][d] = p.v[(size_t)b * p.v_bs + (size_t)hkv * DH + d];
-  }
-  __syncthreads();
-  for (int h = warp; h < 8; h += V2_THREADS / 32) {
-    // sum_d q_d and the full-precision logit of the new token (Template.hpp:1356-1376), log2 domain
-    float s = 0.f, dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float qv = __half2float(q_s[h][lane * 4 + i]);
-      s += qv;
-      dot += qv * __half2float(kv_new[0][lane * 4 + i]);
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, m);
-      dot += __shfl_xor_sync(0xffffffffu, dot, m);
-    }
-    if (lane == 0) { qsum_s[h] = s; cur_logit_s[h] = dot * (0.08838834764831845f * LOG2E); }
-  }
-  const bool writer = owns_current && ((G > 1) || group == 1 || (hq0 == hkv * group));
-  if (writer && warp >= 2 && warp < 4) {
-    const int which = warp - 2;  // 0 = K, 1 = V
-    const int64_t* tab = which ? sv.vtab : sv.ktab;
-    SeqView wv = sv;
-    if (wv.mode == 2) wv.mode = 0;
-    uint8_t* page = reinterpret_cast<uint8_t*>(tab[wv.tab_idx(tl)]);
-    const int slot = tl & 63;
-    __half x[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = kv_new[which][lane * 4 + i];
-    __half* sc = reinterpret_cast<__half*>(page + sv.data_bytes) + sv.rank * TPB + slot;
-    quant_store_token(x, page + (size_t)sv.rank * TPB * (DH / 2) + slot * (DH / 2), sc, sc + sv.hpool * TPB, lane);
-  }
   __syncthreads();
 
   const float qk_scale = 0.08838834764831845f * LOG2E;  // 1/sqrt(128) * log2(e)
   float acc[8][4];
-  float m0 = -1.0e30f, m1 = -1.0e30f, l0 = 0.f, l1 = 0.f, corr0 = 0.f, corr1 = 0.f;
+  float m0 = -1.0e30f, m1 = -1.0e30f, l0 = 0.f, l1 = 0.f, corr0 = 0.f, corr1 = 0.f, sp0 = 0.f, sp1 = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 
   if (warp == 4) {
-    // ================================================================ producer
+    // ================================================================ producer (starts before the prologue)
     if (lane == 0) {
-      int it = 0;
-      for (int v = v0; v < v1; ++v, ++it) {
-        const int s = it % V2_STAGES, ph = (it / V2_STAGES) & 1;
+      int s = 0, ph = 0;
+      for (int v = v0; v < v1; ++v) {
+        // Pages older than the newest one were written at least two decode steps ago and are streamed while the
+        // previous kernel (the qkv GEMM) is still draining; the newest page holds the token appended by the
+        // previous step's attention call, so it is fetched only after the grid dependency resolved.
+        if (v == vis.n - 1) pdl_wait();
         mbar_wait(&empty[s], ph ^ 1);
         const Visit vv = vis.get(v);
         const uint8_t* kp = reinterpret_cast<const uint8_t*>(sv.ktab[vv.tab]);
@@ -338,9 +283,85 @@ kv4_decode_kernel(const AttnParams p, const int G) {
         bulk_g2s(st + 8192 + 128, kp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
         bulk_g2s(st + 8192 + 256, vp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
         bulk_g2s(st + 8192 + 384, vp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
+        if (++s == V2_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else {
+    // ------------------------------------------------------------------ prologue: q/k RoPE, append new K/V
+    pdl_wait();  // q, k, v are the previous kernel's output
+    {
+      const float pos = (float)tl;
+      const int half_rot = p.rotary_dim >> 1;
+      for (int item = tid; item < 9 * (DH / 2); item += 128) {
+        const int h = item / (DH / 2), d = item - h * (DH / 2);
+        if (h < 8 && h >= G) {  // unused head rows of the 8-wide MMA N dimension
+          q_s[h][d] = __float2half_rn(0.f);
+          q_s[h][d + DH / 2] = __float2half_rn(0.f);
+          continue;
+        }
+        const __half* src = (h < 8) ? p.q + (size_t)b * p.q_bs + (size_t)(hq0 + h) * DH
+                                    : p.k + (size_t)b * p.k_bs + (size_t)hkv * DH;
+        __half* dst = (h < 8) ? q_s[h] : kv_new[0];
+        if (d < half_rot) {
+          const float inv_freq = (pos * p.rope_scale) / powf(p.rope_base, (float)(2 * d) / (float)p.rotary_dim);
+          float sn, cs;
+          sincosf(inv_freq, &sn, &cs);
+          const float x = __half2float(src[d]), y = __half2float(src[d + half_rot]);
+          dst[d] = __float2half_rn(cs * x - sn * y);
+          dst[d + half_rot] = __float2half_rn(cs * y + sn * x);
+        } else {
+          const int e = p.rotary_dim + 2 * (d - half_rot);
+          dst[e] = src[e];
+          dst[e + 1] = src[e + 1];
+        }
+      }
+      for (int d = tid; d < DH; d += 128) kv_new[1][d] = p.v[(size_t)b * p.v_bs + (size_t)hkv * DH + d];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int h = warp; h < 8; h += 4) {
+      // Full-precision logit of the new token (Template.hpp:1356-1376, log2 domain), then re-encode q for the
+      // biased-nibble MMAs: odd dims are stored as q/16 because their nibbles enter as 1024 + 16 n.
+      float s = 0.f, dot = 0.f, bias = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = lane * 4 + i;
+        const float qv = __half2float(q_s[h][d]);
+        dot += qv * __half2float(kv_new[0][d]);
+        if (i & 1) {
+          const __half qh = __float2half_rn(qv * 0.0625f);
+          q_s[h][d] = qh;
+          const float qe = __half2float(qh);
+          bias += qe;
+          s += 16.f * qe;
+        } else {
+          bias += qv;
+          s += qv;
+        }
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, m);
+        dot += __shfl_xor_sync(0xffffffffu, dot, m);
+        bias += __shfl_xor_sync(0xffffffffu, bias, m);
+      }
+      if (lane == 0) { qsum_s[h] = s; qbias_s[h] = 1024.f * bias; cur_logit_s[h] = dot * qk_scale; }
+    }
+    const bool writer = owns_current && ((G > 1) || group == 1 || (hq0 == hkv * group));
+    if (writer && warp >= 2) {
+      const int which = warp - 2;  // 0 = K, 1 = V
+      const int64_t* tab = which ? sv.vtab : sv.ktab;
+      SeqView wv = sv;
+      if (wv.mode == 2) wv.mode = 0;
+      uint8_t* page = reinterpret_cast<uint8_t*>(tab[wv.tab_idx(tl)]);
+      const int slot = tl & 63;
+      __half x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = kv_new[which][lane * 4 + i];
+      __half* sc = reinterpret_cast<__half*>(page + sv.data_bytes) + sv.rank * TPB + slot;
+      quant_store_token(x, page + (size_t)sv.rank * TPB * (DH / 2) + slot * (DH / 2), sc, sc + sv.hpool * TPB, lane);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+
     // ================================================================ compute warps
     const int g = lane >> 2, c = lane & 3;
     uint32_t qB[16];
@@ -350,48 +371,53 @@ kv4_decode_kernel(const AttnParams p, const int G) {
       for (int j = 0; j < 4; ++j)
         qB[w * 4 + j] = h2_as_u32(__halves2half2(q_s[g][c * 32 + w * 8 + j], q_s[g][c * 32 + w * 8 + j + 4]));
     const float qs0 = qsum_s[2 * c], qs1 = qsum_s[2 * c + 1];
+    const float qb0 = qbias_s[2 * c], qb1 = qbias_s[2 * c + 1];
     const int base = warp * 16;
     const int tok_a = base + kappa(g), tok_b = base + kappa(g + 8);
-    const int vt0 = base + kappa(2 * c), vt1 = base + kappa(2 * c + 1), vt2 = base + kappa(8 + 2 * c),
-              vt3 = base + kappa(9 + 2 * c);
-    int it = 0;
-    for (int v = v0; v < v1; ++v, ++it) {
-      const int s = it % V2_STAGES, ph = (it / V2_STAGES) & 1;
+    const uint32_t ka_off = tok_a * 64 + c * 16, kb_off = tok_b * 64 + c * 16;
+    const uint32_t v_off0 = 4096 + (base + kappa(2 * c)) * 64 + g * 8, v_off1 = 4096 + (base + kappa(2 * c + 1)) * 64 + g * 8;
+    const uint32_t v_off2 = 4096 + (base + kappa(8 + 2 * c)) * 64 + g * 8, v_off3 = 4096 + (base + kappa(9 + 2 * c)) * 64 + g * 8;
+    int s = 0, ph = 0;
+    for (int v = v0; v < v1; ++v) {
       const Visit vv = vis.get(v);
       mbar_wait(&full[s], ph);
       if (base < vv.hi && base + 16 > vv.lo) {
         const uint8_t* st = ring + s * V2_STAGE_BYTES;
         const __half* ksc = reinterpret_cast<const __half*>(st + 8192);
-        const __half* kzp = ksc + 64;
-        const __half* vsc = ksc + 128;
-        const __half* vzp = ksc + 192;
-        // ---------------- S^T = (K - 8) . Q^T
-        const uint4 ka = *reinterpret_cast<const uint4*>(st + tok_a * 64 + c * 16);
-        const uint4 kb = *reinterpret_cast<const uint4*>(st + tok_b * 64 + c * 16);
-        __half2 na[16], nb[16];
-        {
-          __half2 t[4];
-          nib8_to_h2(ka.x, t); na[0] = t[0]; na[1] = t[1]; na[2] = t[2]; na[3] = t[3];
-          nib8_to_h2(ka.y, t); na[4] = t[0]; na[5] = t[1]; na[6] = t[2]; na[7] = t[3];
-          nib8_to_h2(ka.z, t); na[8] = t[0]; na[9] = t[1]; na[10] = t[2]; na[11] = t[3];
-          nib8_to_h2(ka.w, t); na[12] = t[0]; na[13] = t[1]; na[14] = t[2]; na[15] = t[3];
-          nib8_to_h2(kb.x, t); nb[0] = t[0]; nb[1] = t[1]; nb[2] = t[2]; nb[3] = t[3];
-          nib8_to_h2(kb.y, t); nb[4] = t[0]; nb[5] = t[1]; nb[6] = t[2]; nb[7] = t[3];
-          nib8_to_h2(kb.z, t); nb[8] = t[0]; nb[9] = t[1]; nb[10] = t[2]; nb[11] = t[3];
-          nib8_to_h2(kb.w, t); nb[12] = t[0]; nb[13] = t[1]; nb[14] = t[2]; nb[15] = t[3];
-        }
-        float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+        // ---------------- S^T = (1024 + c n_K) . Q'^T     (bias removed below)
+        const uint4 ka = *reinterpret_cast<const uint4*>(st + ka_off);
+        const uint4 kb = *reinterpret_cast<const uint4*>(st + kb_off);
+        const uint2 w0 = *reinterpret_cast<const uint2*>(st + v_off0);
+        const uint2 w1 = *reinterpret_cast<const uint2*>(st + v_off1);
+        const uint2 w2 = *reinterpret_cast<const uint2*>(st + v_off2);
+        const uint2 w3 = *reinterpret_cast<const uint2*>(st + v_off3);
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t kaw[4] = {ka.x, ka.y, ka.z, ka.w}, kbw[4] = {kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
-        for (int sl = 0; sl < 8; ++sl)
-          mma16816(sacc, h2_as_u32(na[2 * sl]), h2_as_u32(nb[2 * sl]), h2_as_u32(na[2 * sl + 1]),
-                   h2_as_u32(nb[2 * sl + 1]), qB[2 * sl], qB[2 * sl + 1]);
-        const bool va = tok_a >= vv.lo && tok_a < vv.hi, vb = tok_b >= vv.lo && tok_b < vv.hi;
-        const float ksa = __half2float(ksc[tok_a]), kza = __half2float(kzp[tok_a]);
-        const float ksb = __half2float(ksc[tok_b]), kzb = __half2float(kzp[tok_b]);
-        const float la0 = va ? (ksa * sacc[0] + ksa * (8.f - kza) * qs0) * qk_scale : -INFINITY;
-        const float la1 = va ? (ksa * sacc[1] + ksa * (8.f - kza) * qs1) * qk_scale : -INFINITY;
-        const float lb0 = vb ? (ksb * sacc[2] + ksb * (8.f - kzb) * qs0) * qk_scale : -INFINITY;
-        const float lb1 = vb ? (ksb * sacc[3] + ksb * (8.f - kzb) * qs1) * qk_scale : -INFINITY;
+        for (int w = 0; w < 4; ++w) {
+          uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+          const uint32_t ta = kaw[w] >> 8, tb = kbw[w] >> 8;
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(a0) : "r"(kaw[w]));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(a1) : "r"(kaw[w]));
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(a2) : "r"(ta));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(a3) : "r"(ta));
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(b0) : "r"(kbw[w]));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(b1) : "r"(kbw[w]));
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(b2) : "r"(tb));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(b3) : "r"(tb));
+          // slabs 2w (pairs j = 0,1) and 2w+1 (pairs j = 2,3); two independent accumulator chains
+          mma16816(sa, a0, b0, a1, b1, qB[4 * w], qB[4 * w + 1]);
+          mma16816(sb, a2, b2, a3, b3, qB[4 * w + 2], qB[4 * w + 3]);
+        }
+        const bool full_page = (vv.lo == 0) & (vv.hi == TPB);
+        const bool va = full_page || (tok_a >= vv.lo && tok_a < vv.hi);
+        const bool vb = full_page || (tok_b >= vv.lo && tok_b < vv.hi);
+        const float ksa = __half2float(ksc[tok_a]), kza = __half2float(ksc[64 + tok_a]);
+        const float ksb = __half2float(ksc[tok_b]), kzb = __half2float(ksc[64 + tok_b]);
+        const float la0 = va ? ksa * ((sa[0] + sb[0]) - qb0 - kza * qs0) * qk_scale : -INFINITY;
+        const float la1 = va ? ksa * ((sa[1] + sb[1]) - qb1 - kza * qs1) * qk_scale : -INFINITY;
+        const float lb0 = vb ? ksb * ((sa[2] + sb[2]) - qb0 - kzb * qs0) * qk_scale : -INFINITY;
+        const float lb1 = vb ? ksb * ((sa[3] + sb[3]) - qb1 - kzb * qs1) * qk_scale : -INFINITY;
         // ---------------- online softmax over the 16 tokens (lanes with equal c share the heads 2c, 2c+1)
         float x0 = fmaxf(la0, lb0), x1 = fmaxf(la1, lb1);
 #pragma unroll
@@ -402,7 +428,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
         const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
         if (__any_sync(0xffffffffu, n0 != m0 || n1 != m1)) {
           const float f0 = ex2(m0 - n0), f1 = ex2(m1 - n1);
-          l0 *= f0; l1 *= f1; corr0 *= f0; corr1 *= f1;
+          l0 *= f0; l1 *= f1; corr0 *= f0; corr1 *= f1; sp0 *= f0; sp1 *= f1;
 #pragma unroll
           for (int j = 0; j < 8; ++j) { acc[j][0] *= f0; acc[j][1] *= f1; acc[j][2] *= f0; acc[j][3] *= f1; }
           m0 = n0; m1 = n1;
@@ -410,21 +436,17 @@ kv4_decode_kernel(const AttnParams p, const int G) {
         const float pa0 = ex2(la0 - m0), pa1 = ex2(la1 - m1), pb0 = ex2(lb0 - m0), pb1 = ex2(lb1 - m1);
         l0 += pa0 + pb0;
         l1 += pa1 + pb1;
-        const float vsa = va ? __half2float(vsc[tok_a]) : 0.f, vza = va ? __half2float(vzp[tok_a]) : 8.f;
-        const float vsb = vb ? __half2float(vsc[tok_b]) : 0.f, vzb = vb ? __half2float(vzp[tok_b]) : 8.f;
-        const float qa0 = pa0 * vsa, qa1 = pa1 * vsa, qb0 = pb0 * vsb, qb1 = pb1 * vsb;
-        corr0 += qa0 * (vza - 8.f) + qb0 * (vzb - 8.f);
-        corr1 += qa1 * (vza - 8.f) + qb1 * (vzb - 8.f);
-        const uint32_t pb_lo = movmatrix_trans(h2_as_u32(__floats2half2_rn(qa0, qa1)));
-        const uint32_t pb_hi = movmatrix_trans(h2_as_u32(__floats2half2_rn(qb0, qb1)));
-        // ---------------- O^T += (V - 8)^T . P'^T
-        const uint2 w0 = *reinterpret_cast<const uint2*>(st + 4096 + vt0 * 64 + g * 8);
-        const uint2 w1 = *reinterpret_cast<const uint2*>(st + 4096 + vt1 * 64 + g * 8);
-        const uint2 w2 = *reinterpret_cast<const uint2*>(st + 4096 + vt2 * 64 + g * 8);
-        const uint2 w3 = *reinterpret_cast<const uint2*>(st + 4096 + vt3 * 64 + g * 8);
-        const __half2 c1032 = __halves2half2(__ushort_as_half(0x6408), __ushort_as_half(0x6408));
-        const __half2 c16th = __halves2half2(__ushort_as_half(0x2c00), __ushort_as_half(0x2c00));
-        const __half2 cm72 = __halves2half2(__ushort_as_half(0xd480), __ushort_as_half(0xd480));
+        const float vsa = va ? __half2float(ksc[128 + tok_a]) : 0.f, vza = va ? __half2float(ksc[192 + tok_a]) : 0.f;
+        const float vsb = vb ? __half2float(ksc[128 + tok_b]) : 0.f, vzb = vb ? __half2float(ksc[192 + tok_b]) : 0.f;
+        const __half2 ha = __floats2half2_rn(pa0 * vsa, pa1 * vsa), hb = __floats2half2_rn(pb0 * vsb, pb1 * vsb);
+        const float2 fa = __half22float2(ha), fb = __half22float2(hb);  // the values the MMA will really use
+        sp0 += fa.x + fb.x;
+        sp1 += fa.y + fb.y;
+        corr0 += fa.x * vza + fb.x * vzb;
+        corr1 += fa.y * vza + fb.y * vzb;
+        const uint32_t pb_lo = movmatrix_trans(h2_as_u32(ha));
+        const uint32_t pb_hi = movmatrix_trans(h2_as_u32(hb));
+        // ---------------- O^T += (1024 + c n_V)^T . P'^T
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t A = j < 4 ? w0.x : w0.y, B = j < 4 ? w1.x : w1.y, Cw = j < 4 ? w2.x : w2.y,
@@ -436,23 +458,22 @@ kv4_decode_kernel(const AttnParams p, const int G) {
           asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(t1) : "r"(u01));
           asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(t2) : "r"(u23));
           asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(t3) : "r"(u23));
-          const uint32_t a0 = h2_as_u32(__hsub2(*reinterpret_cast<__half2*>(&t0), c1032));
-          const uint32_t a1 = h2_as_u32(__hfma2(*reinterpret_cast<__half2*>(&t1), c16th, cm72));
-          const uint32_t a2 = h2_as_u32(__hsub2(*reinterpret_cast<__half2*>(&t2), c1032));
-          const uint32_t a3 = h2_as_u32(__hfma2(*reinterpret_cast<__half2*>(&t3), c16th, cm72));
-          mma16816(acc[j], a0, a1, a2, a3, pb_lo, pb_hi);
+          mma16816(acc[j], t0, t1, t2, t3, pb_lo, pb_hi);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
+      if (++s == V2_STAGES) { s = 0; ph ^= 1; }
     }
-    // per-warp totals: l and corr are per-thread partials over the rows g of equal c
+    // per-warp totals: l, sp and corr are per-thread partials over the rows g of equal c
 #pragma unroll
     for (int k = 4; k <= 16; k <<= 1) {
       l0 += __shfl_xor_sync(0xffffffffu, l0, k);
       l1 += __shfl_xor_sync(0xffffffffu, l1, k);
       corr0 += __shfl_xor_sync(0xffffffffu, corr0, k);
       corr1 += __shfl_xor_sync(0xffffffffu, corr1, k);
+      sp0 += __shfl_xor_sync(0xffffffffu, sp0, k);
+      sp1 += __shfl_xor_sync(0xffffffffu, sp1, k);
     }
   }
   __syncthreads();  // every stage consumed: the ring can be reused as the merge buffer
@@ -464,8 +485,8 @@ kv4_decode_kernel(const AttnParams p, const int G) {
       // acc[j] = O^T[dims 16g+2j (rows g), 16g+2j+1 (rows g+8)][heads 2c, 2c+1]
       float* o0 = obuf + ((warp * 8 + 2 * c) * DH) + 16 * g + 2 * j;
       float* o1 = o0 + DH;
-      o0[0] = acc[j][0] - corr0; o0[1] = acc[j][2] - corr0;
-      o1[0] = acc[j][1] - corr1; o1[1] = acc[j][3] - corr1;
+      o0[0] = (acc[j][0] - 1024.f * sp0) - corr0; o0[1] = (acc[j][2] - 1024.f * sp0) * 0.0625f - corr0;
+      o1[0] = (acc[j][1] - 1024.f * sp1) - corr1; o1[1] = (acc[j][3] - 1024.f * sp1) * 0.0625f - corr1;
     }
     if (g == 0) {
       ml_s[warp][2 * c][0] = m0; ml_s[warp][2 * c][1] = l0;
@@ -560,6 +581,8 @@ OB_DEVICE void quant_store_pairs(const float (&x)[4], uint8_t* row, __half* scal
 }
 
 __global__ void __launch_bounds__(256) kv4_prefill_write_kernel(const PrefillParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_cta = blockDim.x >> 5;
   const int heads_total = p.Hq + 2 * p.Hkv;
@@ -688,8 +711,8 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
     p.part_o = g_part_o[dev]; p.part_ml = g_part_ml[dev]; p.counters = g_att_cnt[dev];
   }
   dim3 grid(n_split, ctas_y, a.B);
-  kv4_decode_kernel<<<grid, V2_THREADS, V2_STAGES * V2_STAGE_BYTES, st>>>(p, G);
-  return cudaGetLastError() == cudaSuccess ? 0 : OB_ERR_CUDA;
+  return launch_pdl(kv4_decode_kernel, grid, dim3(V2_THREADS), (size_t)(V2_STAGES * V2_STAGE_BYTES), st, p, G) == cudaSuccess
+             ? 0 : OB_ERR_CUDA;
 }
 
 }  // namespace ob
@@ -710,8 +733,7 @@ int kv4_prefill_write_run(const KV4PrefillArgs& a, cudaStream_t st) {
   p.rotary_dim = a.rotary_dim; p.rope_base = a.rotary_base; p.rope_scale = a.rotary_scale;
   const long long items = (long long)a.T * (a.Hq + 2 * a.Hkv);
   const int blocks = (int)std::min<long long>((items + 7) / 8, 148LL * 16);
-  kv4_prefill_write_kernel<<<blocks, 256, 0, st>>>(p);
-  return cudaGetLastError() == cudaSuccess ? 0 : OB_ERR_CUDA;
+  return launch_pdl(kv4_prefill_write_kernel, dim3(blocks), dim3(256), 0, st, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
 int padding_offsets_run(int* out, const int* cu_seqlens, int B, int max_seq_len, cudaStream_t st) {

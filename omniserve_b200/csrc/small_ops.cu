@@ -6,6 +6,7 @@
 // kept in registers so HBM sees exactly one read of the input and one write of the output
 // (the reference re-reads the row 2-3x).  Fast-math intrinsics are used where the reference's
 // `--use_fast_math` build uses them so that the INT8 codes agree with the rebuilt reference.
+#include "launch.h"
 #include "ptx.cuh"
 #include "small_ops.h"
 
@@ -62,6 +63,8 @@ template <bool FUSE_SUM>
 __global__ void __launch_bounds__(512) quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out, __half* __restrict__ scale,
                              __half* __restrict__ sum, int H) {
   __shared__ float red[64];
+  pdl_trigger();
+  pdl_wait();
   const size_t row = blockIdx.x;
   const int nvec = H >> 3;
   const uint4* src = reinterpret_cast<const uint4*>(in + row * H);
@@ -103,22 +106,33 @@ __global__ void __launch_bounds__(512) quant_kernel(const __half* __restrict__ i
 // rms_norm_general(_fuse_sum)  (layernorm_kernels.cu:194-331): (x-mean)*rsqrt(mean(x^2)+eps)*gamma,
 // fp16-rounded before amax / sum, per-"reference thread" fp16 partial sums.  blockDim = refblock/8.
 // ------------------------------------------------------------------------------------------------
-template <bool FUSE_SUM>
-__global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __restrict__ in, const __half* __restrict__ gamma,
+// ADD: x = in + delta (fp16 add, like torch's residual add) is formed first and written to hidden_out.
+template <bool FUSE_SUM, bool ADD>
+__global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __restrict__ in, const __half* __restrict__ delta,
+                                     __half* __restrict__ hidden_out, const __half* __restrict__ gamma,
                                      int8_t* __restrict__ out, __half* __restrict__ scale, __half* __restrict__ sum,
                                      int H, float eps) {
   __shared__ float red[64];
+  pdl_trigger();
   const size_t row = blockIdx.x;
   const int nvec = H >> 3;
   const uint4* src = reinterpret_cast<const uint4*>(in + row * H);
   const uint4* gsrc = reinterpret_cast<const uint4*>(gamma);
   V8 v[MAXV];
   float s1 = 0.f, s2 = 0.f;
+  pdl_wait();
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
     if (idx < nvec) {
       v[i].u = ld_nc_v4(src + idx);
+      if (ADD) {
+        V8 dl;
+        dl.u = ld_nc_v4(reinterpret_cast<const uint4*>(delta + row * H) + idx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i].h2[j] = __hadd2(v[i].h2[j], dl.h2[j]);
+        reinterpret_cast<uint4*>(hidden_out + row * H)[idx] = v[i].u;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float f = __half2float(v[i].h[j]);
@@ -171,20 +185,29 @@ __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __rest
 }
 
 // plain rms_norm, fp16 out (layernorm_kernels.cu:335-364): ((half)(x*rstd)) * w in half
-__global__ void __launch_bounds__(512) rmsnorm_f16_kernel(const __half* __restrict__ in, const __half* __restrict__ gamma,
-                                   __half* __restrict__ out, int H, float eps) {
+template <bool ADD>
+__global__ void __launch_bounds__(512) rmsnorm_f16_kernel(const __half* __restrict__ in, const __half* __restrict__ delta,
+                                   const __half* __restrict__ gamma, __half* __restrict__ out, int H, float eps) {
   __shared__ float red[64];
+  pdl_trigger();
   const size_t row = blockIdx.x;
   const int nvec = H >> 3;
   const uint4* src = reinterpret_cast<const uint4*>(in + row * H);
   const uint4* gsrc = reinterpret_cast<const uint4*>(gamma);
   V8 v[MAXV];
   float s2 = 0.f, dummy = 0.f;
+  pdl_wait();
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
     if (idx < nvec) {
       v[i].u = ld_nc_v4(src + idx);
+      if (ADD) {
+        V8 dl;
+        dl.u = ld_nc_v4(reinterpret_cast<const uint4*>(delta + row * H) + idx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i].h2[j] = __hadd2(v[i].h2[j], dl.h2[j]);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float f = __half2float(v[i].h[j]);
@@ -219,6 +242,8 @@ OB_DEVICE __half silu_mul(__half g, __half u) {
 }
 
 __global__ void __launch_bounds__(512) silu_and_mul_kernel(const __half* __restrict__ in, __half* __restrict__ out, int d) {
+  pdl_trigger();
+  pdl_wait();
   const size_t row = blockIdx.x;
   const uint4* g = reinterpret_cast<const uint4*>(in + row * 2 * d);
   const uint4* u = reinterpret_cast<const uint4*>(in + row * 2 * d + d);
@@ -237,6 +262,8 @@ template <bool FUSE_SUM>
 __global__ void __launch_bounds__(512) silu_mul_quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out,
                                       __half* __restrict__ scale, __half* __restrict__ sum, int d) {
   __shared__ float red[64];
+  pdl_trigger();
+  pdl_wait();
   const size_t row = blockIdx.x;
   const int nvec = d >> 3;
   const uint4* g = reinterpret_cast<const uint4*>(in + row * 2 * d);
@@ -281,6 +308,8 @@ __global__ void __launch_bounds__(512) silu_mul_quant_kernel(const __half* __res
 // fp16 residual add (llama_w4a8_unpad.py:425,437 `residual + out_down_proj_act_buffer`)
 __global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out,
                            size_t nvec) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     V8 x, y, o;
     x.u = reinterpret_cast<const uint4*>(a)[i];
@@ -314,13 +343,13 @@ int quant_run(const __half* in, int8_t* out, __half* scale, __half* sum, int T, 
   if (T <= 0) return 0;
   if (int e = check(H)) return e;
   const int th = pick_threads(H >> 3, 4);
-  if (sum) quant_kernel<true><<<T, th, 0, st>>>(in, out, scale, sum, H);
-  else quant_kernel<false><<<T, th, 0, st>>>(in, out, scale, nullptr, H);
-  return OB_LAUNCH_OK();
+  cudaError_t e = sum ? launch_pdl(quant_kernel<true>, dim3(T), dim3(th), 0, st, in, out, scale, sum, H)
+                      : launch_pdl(quant_kernel<false>, dim3(T), dim3(th), 0, st, in, out, scale, (__half*)nullptr, H);
+  return e == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
-int rmsnorm_quant_run(const __half* in, const __half* gamma, int8_t* out, __half* scale, __half* sum, int T, int H,
-                      float eps, cudaStream_t st) {
+int rmsnorm_quant_run(const __half* in, const __half* delta, __half* hidden_out, const __half* gamma, int8_t* out,
+                      __half* scale, __half* sum, int T, int H, float eps, cudaStream_t st) {
   if (T <= 0) return 0;
   // reference block = min(H,1024) rounded up to 32 threads, one element per thread per iteration
   int refblock = std::min(H, 1024);
@@ -328,32 +357,42 @@ int rmsnorm_quant_run(const __half* in, const __half* gamma, int8_t* out, __half
   if (int e = check(H, refblock / 8)) return e;
   if (H % refblock != 0 && H > refblock) return OB_ERR_SHAPE;
   const int th = std::max(32, refblock / 8);
-  if (sum) rmsnorm_quant_kernel<true><<<T, th, 0, st>>>(in, gamma, out, scale, sum, H, eps);
-  else rmsnorm_quant_kernel<false><<<T, th, 0, st>>>(in, gamma, out, scale, nullptr, H, eps);
-  return OB_LAUNCH_OK();
+  cudaError_t e;
+  const dim3 g(T), b(th);
+  if (delta) {
+    e = sum ? launch_pdl(rmsnorm_quant_kernel<true, true>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps)
+            : launch_pdl(rmsnorm_quant_kernel<false, true>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps);
+  } else {
+    e = sum ? launch_pdl(rmsnorm_quant_kernel<true, false>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps)
+            : launch_pdl(rmsnorm_quant_kernel<false, false>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps);
+  }
+  return e == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
-int rmsnorm_f16_run(const __half* in, const __half* gamma, __half* out, int T, int H, float eps, cudaStream_t st) {
+int rmsnorm_f16_run(const __half* in, const __half* delta, const __half* gamma, __half* out, int T, int H, float eps,
+                    cudaStream_t st) {
   if (T <= 0) return 0;
   if (int e = check(H)) return e;
-  rmsnorm_f16_kernel<<<T, pick_threads(H >> 3, 4), 0, st>>>(in, gamma, out, H, eps);
-  return OB_LAUNCH_OK();
+  const dim3 g(T), b(pick_threads(H >> 3, 4));
+  cudaError_t e = delta ? launch_pdl(rmsnorm_f16_kernel<true>, g, b, 0, st, in, delta, gamma, out, H, eps)
+                        : launch_pdl(rmsnorm_f16_kernel<false>, g, b, 0, st, in, delta, gamma, out, H, eps);
+  return e == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
 int silu_and_mul_run(const __half* in, __half* out, int T, int d, cudaStream_t st) {
   if (T <= 0) return 0;
   if (d <= 0 || (d & 7)) return OB_ERR_SHAPE;
-  silu_and_mul_kernel<<<T, pick_threads(d >> 3, 4), 0, st>>>(in, out, d);
-  return OB_LAUNCH_OK();
+  return launch_pdl(silu_and_mul_kernel, dim3(T), dim3(pick_threads(d >> 3, 4)), 0, st, in, out, d) == cudaSuccess
+             ? 0 : OB_ERR_CUDA;
 }
 
 int silu_mul_quant_run(const __half* in, int8_t* out, __half* scale, __half* sum, int T, int d, cudaStream_t st) {
   if (T <= 0) return 0;
   if (int e = check(d)) return e;
   const int th = pick_threads(d >> 3, 4);
-  if (sum) silu_mul_quant_kernel<true><<<T, th, 0, st>>>(in, out, scale, sum, d);
-  else silu_mul_quant_kernel<false><<<T, th, 0, st>>>(in, out, scale, nullptr, d);
-  return OB_LAUNCH_OK();
+  cudaError_t e = sum ? launch_pdl(silu_mul_quant_kernel<true>, dim3(T), dim3(th), 0, st, in, out, scale, sum, d)
+                      : launch_pdl(silu_mul_quant_kernel<false>, dim3(T), dim3(th), 0, st, in, out, scale, (__half*)nullptr, d);
+  return e == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
 int add_run(const __half* a, const __half* b, __half* out, size_t n, cudaStream_t st) {
@@ -361,8 +400,7 @@ int add_run(const __half* a, const __half* b, __half* out, size_t n, cudaStream_
   if (n & 7) return OB_ERR_SHAPE;
   const size_t nvec = n >> 3;
   const int blocks = (int)std::min<size_t>((nvec + 255) / 256, 148 * 8);
-  add_kernel<<<blocks, 256, 0, st>>>(a, b, out, nvec);
-  return OB_LAUNCH_OK();
+  return launch_pdl(add_kernel, dim3(blocks), dim3(256), 0, st, a, b, out, nvec) == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
 }  // namespace ob

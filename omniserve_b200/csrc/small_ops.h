@@ -8,9 +8,11 @@
 
 namespace ob {
 int quant_run(const __half* in, int8_t* out, __half* scale, __half* sum /*nullable*/, int T, int H, cudaStream_t st);
-int rmsnorm_quant_run(const __half* in, const __half* gamma, int8_t* out, __half* scale, __half* sum /*nullable*/,
-                      int T, int H, float eps, cudaStream_t st);
-int rmsnorm_f16_run(const __half* in, const __half* gamma, __half* out, int T, int H, float eps, cudaStream_t st);
+// delta / hidden_out nullable: when given, x = in + delta is formed first (fp16) and stored to hidden_out
+int rmsnorm_quant_run(const __half* in, const __half* delta, __half* hidden_out, const __half* gamma, int8_t* out,
+                      __half* scale, __half* sum /*nullable*/, int T, int H, float eps, cudaStream_t st);
+int rmsnorm_f16_run(const __half* in, const __half* delta /*nullable*/, const __half* gamma, __half* out, int T, int H,
+                    float eps, cudaStream_t st);
 int silu_and_mul_run(const __half* in, __half* out, int T, int d, cudaStream_t st);
 int silu_mul_quant_run(const __half* in, int8_t* out, __half* scale, __half* sum /*nullable*/, int T, int d,
                        cudaStream_t st);

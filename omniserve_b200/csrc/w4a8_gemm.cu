@@ -20,6 +20,7 @@
 // every CTA an equal contiguous range of K-blocks so that small-M (decode) problems fill all SMs; tiles
 // that span CTAs are summed exactly in INT32 with cp.reduce.async.bulk (.add.s32) into an L2-resident
 // workspace and finished by the last contributor.
+#include "launch.h"
 #include "ptx.cuh"
 #include "w4a8_gemm.h"
 
@@ -118,6 +119,20 @@ struct SegIter {
   }
 };
 
+// Flat iteration over this CTA's K-blocks (tile, kb).
+struct KbIter {
+  SegIter it;
+  Seg sg;
+  int kb;
+  OB_DEVICE void init(const GemmParams& p) { it.init(p); sg.kb0 = sg.kb1 = 0; kb = 0; }
+  OB_DEVICE bool next() {
+    if (kb + 1 < sg.kb1 && sg.kb1 > sg.kb0) { ++kb; return true; }
+    if (!it.next(sg)) return false;
+    kb = sg.kb0;
+    return true;
+  }
+};
+
 OB_DEVICE void tile_coords(const GemmParams& p, int tile, int& nt, int& mt) {
   if (p.mode == 0) {
     int per_group = p.group_m * p.n_tiles;
@@ -160,6 +175,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&act_map);
@@ -184,31 +200,47 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p
 
   if (warp == 0) {
     // ================================================================ producer
+    // Weights never depend on the previous kernel: with programmatic dependent launch the packed-W (and s2)
+    // tiles of the first pipeline stages are already in flight while the predecessor is still draining; only
+    // the activation tiles wait for it.
     if (lane == 0) {
-      SegIter it;
-      it.init(p);
-      Seg sg;
-      int stage = 0, phase = 0;
-      while (it.next(sg)) {
+      auto issue_w = [&](int stage, int tile, int kb) {
         int nt, mt;
-        tile_coords(p, sg.tile, nt, mt);
+        tile_coords(p, tile, nt, mt);
         const int n32_0 = nt * 4;
         const int n32_cnt = min(4, p.N / 32 - n32_0);
         const int n_cnt = n32_cnt * 32;
-        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint32_t tx = C::B_STAGE + n32_cnt * 2048 + (PER_GROUP ? 2 * n_cnt : 0);
-          mbar_arrive_expect_tx(&full[stage], tx);
-          tma_load_2d(sB + stage * C::B_STAGE, &act_map, kb * BK, mt * BN, &full[stage]);
-          const int8_t* wsrc = p.qweight + ((size_t)n32_0 * k32_per_row + (size_t)kb * 4) * 512;
-          for (int i = 0; i < n32_cnt; ++i)
-            bulk_g2s(sW + stage * W_STAGE + i * 2048, wsrc + (size_t)i * k32_per_row * 512, 2048, &full[stage]);
-          if (PER_GROUP) {
-            bulk_g2s(sS2 + stage * C::S2_STAGE, p.s2_scales + (size_t)kb * p.N + nt * BM, n_cnt, &full[stage]);
-            bulk_g2s(sS2 + stage * C::S2_STAGE + 128, p.s2_zeros + (size_t)kb * p.N + nt * BM, n_cnt, &full[stage]);
-          }
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        const uint32_t tx = C::B_STAGE + n32_cnt * 2048 + (PER_GROUP ? 2 * n_cnt : 0);
+        mbar_arrive_expect_tx(&full[stage], tx);
+        const int8_t* wsrc = p.qweight + ((size_t)n32_0 * k32_per_row + (size_t)kb * 4) * 512;
+        for (int i = 0; i < n32_cnt; ++i)
+          bulk_g2s(sW + stage * W_STAGE + i * 2048, wsrc + (size_t)i * k32_per_row * 512, 2048, &full[stage]);
+        if (PER_GROUP) {
+          bulk_g2s(sS2 + stage * C::S2_STAGE, p.s2_scales + (size_t)kb * p.N + nt * BM, n_cnt, &full[stage]);
+          bulk_g2s(sS2 + stage * C::S2_STAGE + 128, p.s2_zeros + (size_t)kb * p.N + nt * BM, n_cnt, &full[stage]);
         }
+      };
+      KbIter pre_it;
+      pre_it.init(p);
+      int pre = 0;
+      while (pre < C::STAGES && pre_it.next()) {
+        issue_w(pre, pre_it.sg.tile, pre_it.kb);
+        ++pre;
+      }
+      pdl_wait();
+      KbIter it;
+      it.init(p);
+      int stage = 0, phase = 0, idx = 0;
+      while (it.next()) {
+        if (idx >= pre) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          issue_w(stage, it.sg.tile, it.kb);
+        }
+        int nt, mt;
+        tile_coords(p, it.sg.tile, nt, mt);
+        tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, mt * BN, &full[stage]);
+        ++idx;
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -296,6 +328,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p
     int acc = 0, acc_phase = 0;
     __half* stage16 = reinterpret_cast<__half*>(sStage);
     int32_t* stage32 = reinterpret_cast<int32_t*>(sStage);
+    pdl_wait();  // ascales / a_ssums come from the previous kernel; `out` may still be read by it
     while (it.next(sg)) {
       int nt, mt;
       tile_coords(p, sg.tile, nt, mt);
@@ -497,8 +530,7 @@ static int launch(const CUtensorMap& map, GemmParams& p, int grid, cudaStream_t 
       return OB_ERR_CUDA;
     attr_done = true;
   }
-  kern<<<grid, NUM_THREADS, C::SMEM_TOTAL, st>>>(map, p);
-  return cudaGetLastError() == cudaSuccess ? 0 : OB_ERR_CUDA;
+  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, map, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
 int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {

@@ -174,6 +174,7 @@ class LlamaW4A8:
         self.kv_size = self.hkv * cfg.head_dim
         self.inter = cfg.intermediate_size // tp_size
         self.fuse_silu_quant = fuse_silu_quant
+        self.fuse_add_norm = hasattr(self.ops.layernorm_ops, "add_rms_norm_general")
         self.act_sum = cfg.group_size == -1
         gen = torch.Generator().manual_seed(seed * 1000 + tp_rank)
         gen_rep = torch.Generator().manual_seed(seed * 1000 + 999)  # replicated parameters: same on every rank
@@ -222,20 +223,36 @@ class LlamaW4A8:
             torch.distributed.all_reduce(t, group=self.pg)
 
     # ------------------------------------------------------------------ one decoder layer
-    def _layer(self, li: int, hidden, out_hidden, T: int, is_prompt: bool, meta):
+    def _norm_quant(self, out_i8, hidden, delta, hidden_out, weight, sm, sc):
+        """rms_norm_general(_fuse_sum) of (hidden [+ delta]).  With our ops the residual add of
+        llama_w4a8_unpad.py:425,437 is fused into the norm (bit-identical to torch.add + norm); with the
+        reference's ops it is a separate torch.add like in the reference.  Returns the tensor holding hidden+delta."""
+        lo, eps = self.ops.layernorm_ops, self.cfg.rms_norm_eps
+        if delta is not None:
+            if self.fuse_add_norm:
+                lo.add_rms_norm_general(out_i8, hidden, delta, hidden_out, weight, sm if self.act_sum else None, sc, eps)
+                return hidden_out
+            torch.add(hidden, delta, out=hidden_out)
+            hidden = hidden_out
+        if self.act_sum:
+            lo.rms_norm_general_fuse_sum(out_i8, hidden, weight, sm, sc, eps, True)
+        else:
+            lo.rms_norm_general(out_i8, hidden, weight, sc, eps, True)
+        return hidden
+
+    def _layer(self, li: int, hidden, delta, T: int, is_prompt: bool, meta):
+        """hidden (+ delta, the previous layer's not-yet-added MLP output) -> returns (hidden', delta')."""
         cfg, ly, b = self.cfg, self.layers[li], self.buf
-        layernorm_ops, fused_kernels, activation_ops = self.ops.layernorm_ops, self.ops.fused_kernels, self.ops.activation_ops
+        fused_kernels, activation_ops = self.ops.fused_kernels, self.ops.activation_ops
         fused_attention_fine_grained_dense = self.ops.fused_attention_fine_grained_dense
         fused_attention_pure_dense = self.ops.fused_attention_pure_dense
         qh = b.quantized_hidden_states_buffer[:T]
         sc, sm = b.quantized_scale_buffer[:T], b.quantized_sum_buffer[:T]
         qkv = b.qkv_proj_act_buffer[:T]
         od = b.out_down_proj_act_buffer[:T]
-        # 1. input_layernorm -> int8 (+sum)     (llama_w4a8_unpad.py:416-421, layernorm.py:86-101)
-        if self.act_sum:
-            layernorm_ops.rms_norm_general_fuse_sum(qh, hidden, ly["input_layernorm"], sm, sc, cfg.rms_norm_eps, True)
-        else:
-            layernorm_ops.rms_norm_general(qh, hidden, ly["input_layernorm"], sc, cfg.rms_norm_eps, True)
+        ha, hb = b.hidden_a[:T], b.hidden_b[:T]
+        # 1. (residual add of the previous MLP +) input_layernorm -> int8 (+sum)  (llama:416-421, layernorm.py:86-101)
+        h1 = self._norm_quant(qh, hidden, delta, ha, ly["input_layernorm"], sm, sc)
         # 2. qkv_proj
         ly["qkv_proj"](qh, sc, sm, qkv)
         q3 = qkv[:, : self.q_size].view(T, self.hq, cfg.head_dim)
@@ -259,17 +276,12 @@ class LlamaW4A8:
             fused_kernels.invoke_quant_fuse_sum(qa, attn, sm, sc)
         else:
             fused_kernels.invoke_quant(qa, attn, sc)
-        # 5. o_proj (row-parallel) -> all-reduce -> residual add
+        # 5. o_proj (row-parallel) -> all-reduce
         ly["o_proj"](qa, sc, sm, od)
         self._all_reduce(od)
-        mid = meta["mid"]
-        torch.add(hidden, od, out=mid)
-        # 7. post_attention_layernorm
-        if self.act_sum:
-            layernorm_ops.rms_norm_general_fuse_sum(qh, mid, ly["post_attention_layernorm"], sm, sc, cfg.rms_norm_eps, True)
-        else:
-            layernorm_ops.rms_norm_general(qh, mid, ly["post_attention_layernorm"], sc, cfg.rms_norm_eps, True)
-        # 8-10. MLP (llama:83-112): gate_up -> silu*mul -> quant -> down
+        # 6-7. residual add + post_attention_layernorm
+        h2 = self._norm_quant(qh, h1, od, hb, ly["post_attention_layernorm"], sm, sc)
+        # 8-10. MLP (llama:83-112): gate_up -> silu*mul -> quant -> down (row-parallel) -> all-reduce
         gu = b.gate_up_proj_act_buffer[:T]
         ly["gate_up_proj"](qh, sc, sm, gu)
         qm = b.quantized_mlp_act_buffer[:T]
@@ -284,23 +296,30 @@ class LlamaW4A8:
                 fused_kernels.invoke_quant(qm, tmp, sc)
         ly["down_proj"](qm, sc, sm, od)
         self._all_reduce(od)
-        torch.add(mid, od, out=out_hidden)
+        return h2, od  # the add of `od` is folded into the next norm
 
     # ------------------------------------------------------------------ whole model
     def _run_layers(self, hidden0, T, is_prompt, meta):
-        b = self.buf
-        cur = hidden0
-        meta["mid"] = b.hidden_b[:T]
-        nxt = b.hidden_a[:T]
+        cur, delta = hidden0, None
         for li in range(self.cfg.num_hidden_layers):
-            self._layer(li, cur, nxt, T, is_prompt, meta)
-            cur = nxt  # hidden_a is rewritten in place each layer (input of layer li+1 is read before its write)
-        return cur
+            cur, delta = self._layer(li, cur, delta, T, is_prompt, meta)
+        return cur, delta
 
-    def _sample(self, hidden_last):
-        """final rms_norm + vocab-parallel lm_head + argmax (torch, as in the reference sampler)."""
+    def _final_hidden(self, hidden, delta):
+        """hidden + delta (the last layer's MLP output), materialised (prefill gathers rows from it)."""
+        out = torch.empty_like(hidden)
+        torch.add(hidden, delta, out=out)
+        return out
+
+    def _sample(self, hidden_last, delta=None):
+        """final rms_norm (+ last residual add) + vocab-parallel lm_head + argmax (torch, as in the reference)."""
         x = torch.empty_like(hidden_last)
-        self.ops.layernorm_ops.rms_norm(x, hidden_last, self.norm_weight, self.cfg.rms_norm_eps, False)
+        if delta is not None and self.fuse_add_norm:
+            self.ops.layernorm_ops.add_rms_norm(x, hidden_last, delta, self.norm_weight, self.cfg.rms_norm_eps)
+        else:
+            if delta is not None:
+                hidden_last = self._final_hidden(hidden_last, delta)
+            self.ops.layernorm_ops.rms_norm(x, hidden_last, self.norm_weight, self.cfg.rms_norm_eps, False)
         logits = torch.matmul(x, self.lm_head.t())
         val, idx = logits.max(dim=-1)
         if self.tp_size == 1:
@@ -338,8 +357,9 @@ class LlamaW4A8:
         self.kv.tables = [t[seq_offset: seq_offset + B] for t in saved]
         try:
             h0 = self.embed_tokens[tokens]
-            h = self._run_layers(h0, T, True, meta)
-            last = h[(cu[1:] - 1).long()]
+            h, delta = self._run_layers(h0, T, True, meta)
+            self.last_hidden = self._final_hidden(h, delta)  # kept for tests
+            last = self.last_hidden[(cu[1:] - 1).long()]
             nxt = self._sample(last)
         finally:
             self.kv.tables = saved
@@ -357,8 +377,9 @@ class LlamaW4A8:
         if not self.fuse_silu_quant:
             meta["silu_tmp"] = self._silu_tmp
         h0 = self.embed_tokens[tokens]
-        h = self._run_layers(h0, B, False, meta)
-        return self._sample(h)
+        h, delta = self._run_layers(h0, B, False, meta)
+        self.last_decode_state = (h, delta)
+        return self._sample(h, delta)
 
     def prepare_decode(self):
         if not self.fuse_silu_quant:
@@ -399,5 +420,5 @@ class DecodeGraph:
 
 def kernel_launches_per_decode_step(cfg: LlamaConfig, fuse_silu_quant: bool = True) -> int:
     """Count of OUR kernels launched per decode step (torch's embedding/add/matmul/argmax not included)."""
-    per_layer = 2 + 4 + 1 + 1 + (1 if fuse_silu_quant else 2)  # norms, gemms, attention, quant, silu(+quant)
-    return per_layer * cfg.num_hidden_layers + 1  # + final rms_norm
+    per_layer = 2 + 4 + 1 + 1 + (1 if fuse_silu_quant else 2)  # (add+)norms, gemms, attention, quant, silu(+quant)
+    return per_layer * cfg.num_hidden_layers + 1  # + final (add+)rms_norm
