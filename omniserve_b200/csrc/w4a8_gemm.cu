@@ -119,16 +119,19 @@ struct SegIter {
   }
 };
 
-// Flat iteration over this CTA's K-blocks (tile, kb).
+OB_DEVICE void tile_coords(const struct GemmParams& p, int tile, int& nt, int& mt);
+
+// Flat iteration over this CTA's K-blocks (tile, kb); tile coordinates are recomputed only per segment.
 struct KbIter {
   SegIter it;
   Seg sg;
-  int kb;
-  OB_DEVICE void init(const GemmParams& p) { it.init(p); sg.kb0 = sg.kb1 = 0; kb = 0; }
-  OB_DEVICE bool next() {
+  int kb, nt, mt;
+  OB_DEVICE void init(const GemmParams& p) { it.init(p); sg.kb0 = sg.kb1 = 0; kb = 0; nt = mt = 0; }
+  OB_DEVICE bool next(const GemmParams& p) {
     if (kb + 1 < sg.kb1 && sg.kb1 > sg.kb0) { ++kb; return true; }
     if (!it.next(sg)) return false;
     kb = sg.kb0;
+    tile_coords(p, sg.tile, nt, mt);
     return true;
   }
 };
@@ -204,9 +207,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p
     // tiles of the first pipeline stages are already in flight while the predecessor is still draining; only
     // the activation tiles wait for it.
     if (lane == 0) {
-      auto issue_w = [&](int stage, int tile, int kb) {
-        int nt, mt;
-        tile_coords(p, tile, nt, mt);
+      auto issue_w = [&](int stage, int nt, int kb) {
         const int n32_0 = nt * 4;
         const int n32_cnt = min(4, p.N / 32 - n32_0);
         const int n_cnt = n32_cnt * 32;
@@ -223,22 +224,20 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p
       KbIter pre_it;
       pre_it.init(p);
       int pre = 0;
-      while (pre < C::STAGES && pre_it.next()) {
-        issue_w(pre, pre_it.sg.tile, pre_it.kb);
+      while (pre < C::STAGES && pre_it.next(p)) {
+        issue_w(pre, pre_it.nt, pre_it.kb);
         ++pre;
       }
       pdl_wait();
       KbIter it;
       it.init(p);
       int stage = 0, phase = 0, idx = 0;
-      while (it.next()) {
+      while (it.next(p)) {
         if (idx >= pre) {
           mbar_wait(&empty[stage], phase ^ 1);
-          issue_w(stage, it.sg.tile, it.kb);
+          issue_w(stage, it.nt, it.kb);
         }
-        int nt, mt;
-        tile_coords(p, it.sg.tile, nt, mt);
-        tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, mt * BN, &full[stage]);
+        tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, it.mt * BN, &full[stage]);
         ++idx;
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }

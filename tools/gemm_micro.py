@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Graph-timed W4A8 GEMM micro-benchmarks: separates fixed per-launch cost, per-K-block cost and split-K cost."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from omniserve_b200 import _lib as L  # noqa: E402
+
+dev = "cuda"
+torch.cuda.set_device(0)
+NSETS = 16
+
+
+def run(M, N, K, mode=-1, bn=0, ctas=0, tag=""):
+    ws = [torch.randint(-128, 128, (N, K // 2), dtype=torch.int8, device=dev) for _ in range(NSETS)]
+    x = torch.randint(-127, 128, (M, K), dtype=torch.int8, device=dev)
+    s1 = torch.full((N,), 0.01, dtype=torch.float16, device=dev)
+    sz = torch.full((N,), 0.08, dtype=torch.float16, device=dev)
+    sa = torch.full((M,), 0.02, dtype=torch.float16, device=dev)
+    ss = torch.full((M,), 0.1, dtype=torch.float16, device=dev)
+    out = torch.empty((M, N), dtype=torch.float16, device=dev)
+
+    def launch_all():
+        for w in ws:
+            c = L.lib().ob_w4a8_gemm_ex(0, L.ptr(x), L.ptr(w), 0, 0, L.ptr(s1), L.ptr(sa), L.ptr(sz), L.ptr(ss), L.ptr(out),
+                                        M, N, K, N, bn, mode, ctas, L.stream())
+            assert c == 0
+    launch_all()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        launch_all()
+    best = 1e9
+    for _ in range(5):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    us = best / NSETS * 1e3
+    by = N * K // 2
+    print(f"{tag:28s} M={M:5d} N={N:6d} K={K:6d} mode={mode:2d} bn={bn:3d} ctas={ctas:3d}: {us:8.2f} us  "
+          f"{by / us / 1e3:8.1f} GB/s  {2.0 * M * N * K / us / 1e6:8.1f} TOPS", flush=True)
+
+
+if __name__ == "__main__":
+    run(64, 18944, 128, mode=0, tag="fixed cost (148 tiles,1kb)")
+    run(64, 18944, 1024, mode=0, tag="148 tiles x 8 kb, no split")
+    run(64, 18944, 4096, mode=0, tag="148 tiles x 32 kb, no split")
+    run(64, 18944, 14336, mode=0, tag="148 tiles x 112 kb, no split")
+    run(64, 4096, 4096, mode=0, tag="o_proj, 32 CTAs no split")
+    run(64, 4096, 4096, mode=1, tag="o_proj stream-K")
+    run(64, 6144, 4096, mode=1, tag="qkv stream-K")
+    run(64, 28672, 4096, mode=1, tag="gate_up stream-K")
+    run(64, 28672, 4096, mode=0, tag="gate_up tiles (224)")
+    run(64, 4096, 14336, mode=1, tag="down stream-K")
+    run(16, 4096, 4096, mode=1, tag="o_proj M=16")
+    run(128, 28672, 4096, tag="gate_up M=128")
+    run(8192, 6144, 4096, tag="prefill qkv")
+    run(8192, 28672, 4096, tag="prefill gate_up")
+    run(8192, 4096, 14336, tag="prefill down")
