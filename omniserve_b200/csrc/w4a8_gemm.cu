@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <unordered_map>
 
 namespace ob {
@@ -76,6 +77,7 @@ struct GemmParams {
   int mode;                 // 0 = DP, 1 = SK
   int units_per_cta;        // SK: K-blocks per CTA
   int group_m;              // DP raster: m-tiles per L2 group
+  int dbg;                  // timing experiments only (OB_GEMM_DBG): 1 = no wait::st, 2 = no unpack, 4 = no MMA
 };
 
 struct Seg {
@@ -158,7 +160,8 @@ OB_DEVICE uint32_t vadd4(uint32_t a, uint32_t b) {
 
 template <int BN, bool PER_GROUP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p) {
+w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_constant__ CUtensorMap w_map,
+                 const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -182,6 +185,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&act_map);
+    tma_prefetch_desc(&w_map);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -202,43 +206,37 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p
   const int k32_per_row = p.K / 32;
 
   if (warp == 0) {
-    // ================================================================ producer
-    // Weights never depend on the previous kernel: with programmatic dependent launch the packed-W (and s2)
-    // tiles of the first pipeline stages are already in flight while the predecessor is still draining; only
-    // the activation tiles wait for it.
+    // ================================================================ weight producer
+    // One 3-D TMA per stage brings the 4 (n32) x 4 (k32) x 512 B packed-weight blocks of the tile's K-block
+    // (the reference layout [N/32][K/32][512 B] viewed as a tensor of 8-byte elements).  Weights never depend on
+    // the previous kernel, so under programmatic dependent launch they stream while it is still draining.
     if (lane == 0) {
-      auto issue_w = [&](int stage, int nt, int kb) {
-        const int n32_0 = nt * 4;
-        const int n32_cnt = min(4, p.N / 32 - n32_0);
-        const int n_cnt = n32_cnt * 32;
-        const uint32_t tx = C::B_STAGE + n32_cnt * 2048 + (PER_GROUP ? 2 * n_cnt : 0);
-        mbar_arrive_expect_tx(&full[stage], tx);
-        const int8_t* wsrc = p.qweight + ((size_t)n32_0 * k32_per_row + (size_t)kb * 4) * 512;
-        for (int i = 0; i < n32_cnt; ++i)
-          bulk_g2s(sW + stage * W_STAGE + i * 2048, wsrc + (size_t)i * k32_per_row * 512, 2048, &full[stage]);
+      KbIter it;
+      it.init(p);
+      int stage = 0, phase = 0;
+      while (it.next(p)) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        const int n_cnt = min(BM, p.N - it.nt * BM);
+        mbar_arrive_expect_tx(&full[stage], C::B_STAGE + W_STAGE + (PER_GROUP ? 2 * n_cnt : 0));
+        tma_load_3d(sW + stage * W_STAGE, &w_map, 0, it.kb * 4, it.nt * 4, &full[stage]);
         if (PER_GROUP) {
-          bulk_g2s(sS2 + stage * C::S2_STAGE, p.s2_scales + (size_t)kb * p.N + nt * BM, n_cnt, &full[stage]);
-          bulk_g2s(sS2 + stage * C::S2_STAGE + 128, p.s2_zeros + (size_t)kb * p.N + nt * BM, n_cnt, &full[stage]);
+          bulk_g2s(sS2 + stage * C::S2_STAGE, p.s2_scales + (size_t)it.kb * p.N + it.nt * BM, n_cnt, &full[stage]);
+          bulk_g2s(sS2 + stage * C::S2_STAGE + 128, p.s2_zeros + (size_t)it.kb * p.N + it.nt * BM, n_cnt, &full[stage]);
         }
-      };
-      KbIter pre_it;
-      pre_it.init(p);
-      int pre = 0;
-      while (pre < C::STAGES && pre_it.next(p)) {
-        issue_w(pre, pre_it.nt, pre_it.kb);
-        ++pre;
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+    }
+  } else if (warp == 3) {
+    // ================================================================ activation producer (own warp: TMA issue
+    // is slow per thread, two issuers double the rate); these tiles are the previous kernel's output.
+    if (lane == 0) {
       pdl_wait();
       KbIter it;
       it.init(p);
-      int stage = 0, phase = 0, idx = 0;
+      int stage = 0, phase = 0;
       while (it.next(p)) {
-        if (idx >= pre) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          issue_w(stage, it.nt, it.kb);
-        }
+        mbar_wait(&empty[stage], phase ^ 1);
         tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, it.mt * BN, &full[stage]);
-        ++idx;
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -260,9 +258,11 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p
         if (lane == 0) {
           const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sB + stage * C::B_STAGE));
           const uint32_t a_tmem = tmem_base + C::TMEM_A_BASE + stage * A_COLS_PER_STAGE;
+          if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
-            umma_i8_ts(d_tmem, a_tmem + a * 8, bdesc + (uint64_t)(a * 2), idesc, (kb > sg.kb0 || a > 0) ? 1u : 0u);
+            for (int a = 0; a < 4; ++a)
+              umma_i8_ts(d_tmem, a_tmem + a * 8, bdesc + (uint64_t)(a * 2), idesc, (kb > sg.kb0 || a > 0) ? 1u : 0u);
+          }
           umma_commit(&empty[stage]);
           if (kb == sg.kb1 - 1) umma_commit(&acc_full[acc]);
         }
@@ -281,6 +281,12 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p
     while (it.next(sg)) {
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
         mbar_wait(&full[stage], phase);
+        if (p.dbg & 2) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
         const uint8_t* wsm = sW + stage * W_STAGE + q * 2048 + lane * 16;
         uint32_t sc[4], zr[4];
         if (PER_GROUP) {
@@ -310,7 +316,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const GemmParams p
           tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
           tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
         }
-        tmem_st_wait();
+        if (!(p.dbg & 1)) tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[stage]);
@@ -503,6 +509,29 @@ static int make_act_map(CUtensorMap* out, const void* ptr, int M, int K, int BN)
   return 0;
 }
 
+static int make_w_map(CUtensorMap* out, const void* ptr, int N, int K) {
+  static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  MapKey key{ptr, N, K, -1};
+  auto f = cache.find(key);
+  if (f != cache.end()) { *out = f->second; return 0; }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return OB_ERR_DRIVER;
+  // [N/32][K/32][512 B] as 8-byte elements: dims (fastest first) {64, K/32, N/32}
+  cuuint64_t dims[3] = {64, (cuuint64_t)(K / 32), (cuuint64_t)(N / 32)};
+  cuuint64_t strides[2] = {512, (cuuint64_t)(K / 32) * 512};
+  cuuint32_t box[3] = {64, 4, 4};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return OB_ERR_DRIVER;
+  if (cache.size() > 8192) cache.clear();
+  cache[key] = *out;
+  return 0;
+}
+
 static int g_num_sms = 0;
 static int32_t* g_ws[16] = {nullptr};
 static int32_t* g_cnt[16] = {nullptr};
@@ -520,7 +549,7 @@ static int ensure_workspace(int dev, int sms) {
 }
 
 template <int BN, bool PG>
-static int launch(const CUtensorMap& map, GemmParams& p, int grid, cudaStream_t st) {
+static int launch(const CUtensorMap& map, const CUtensorMap& wmap, GemmParams& p, int grid, cudaStream_t st) {
   using C = Cfg<BN>;
   auto kern = w4a8_gemm_kernel<BN, PG>;
   static bool attr_done = false;
@@ -529,7 +558,7 @@ static int launch(const CUtensorMap& map, GemmParams& p, int grid, cudaStream_t 
       return OB_ERR_CUDA;
     attr_done = true;
   }
-  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, map, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
+  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, map, wmap, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
 int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
@@ -547,6 +576,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   int BN = a.M <= 16 ? 16 : a.M <= 32 ? 32 : a.M <= 64 ? 64 : 128;
   if (a.force_bn > 0) BN = a.force_bn;
   GemmParams p{};
+  { const char* e = getenv("OB_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.qweight = a.qweight; p.s2_scales = a.s2_scales; p.s2_zeros = a.s2_zeros;
   p.wscales = a.wscales; p.ascales = a.ascales; p.w_szs = a.w_szs; p.a_ssums = a.a_ssums;
   p.out = a.out_feats; p.ws = g_ws[dev]; p.counters = g_cnt[dev];
@@ -570,9 +600,11 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   }
   CUtensorMap map;
   if (int e = make_act_map(&map, a.in_feats, a.M, a.K, BN)) return e;
+  CUtensorMap wmap;
+  if (int e = make_w_map(&wmap, a.qweight, a.N, a.K)) return e;
 #define OB_LAUNCH(bn)                                                              \
   case bn:                                                                         \
-    return per_group ? launch<bn, true>(map, p, grid, st) : launch<bn, false>(map, p, grid, st);
+    return per_group ? launch<bn, true>(map, wmap, p, grid, st) : launch<bn, false>(map, wmap, p, grid, st);
   switch (BN) {
     OB_LAUNCH(16)
     OB_LAUNCH(32)

@@ -47,6 +47,13 @@ def run(M, N, K, mode=-1, bn=0, ctas=0, tag=""):
           f"{by / us / 1e3:8.1f} GB/s  {2.0 * M * N * K / us / 1e6:8.1f} TOPS", flush=True)
 
 
+if __name__ == "__main__" and os.environ.get("OB_GEMM_DBG"):
+    print("OB_GEMM_DBG =", os.environ["OB_GEMM_DBG"], "(results invalid, timing only)")
+    run(64, 18944, 4096, mode=0, tag="148 tiles x 32 kb, no split")
+    run(64, 18944, 14336, mode=0, tag="148 tiles x 112 kb, no split")
+    run(8192, 6144, 4096, tag="prefill qkv")
+    sys.exit(0)
+
 if __name__ == "__main__":
     run(64, 18944, 128, mode=0, tag="fixed cost (148 tiles,1kb)")
     run(64, 18944, 1024, mode=0, tag="148 tiles x 8 kb, no split")
