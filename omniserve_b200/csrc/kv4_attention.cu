@@ -202,6 +202,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
   __shared__ __align__(16) __half q_s[8][DH];
   __shared__ __align__(16) __half kv_new[2][DH];
   __shared__ float qsum_s[8], qbias_s[8], cur_logit_s[8];
+  __shared__ float rope_cs[DH / 2], rope_sn[DH / 2];
   __shared__ float ml_s[4][8][2];
   __shared__ __align__(8) uint64_t full[V2_STAGES], empty[V2_STAGES];
   __shared__ int flag_s;
@@ -288,9 +289,18 @@ kv4_decode_kernel(const AttnParams p, const int G) {
     }
   } else {
     // ------------------------------------------------------------------ prologue: q/k RoPE, append new K/V
-    pdl_wait();  // q, k, v are the previous kernel's output
+    // cos/sin depend on (position, pair index) only: 64 accurate powf/sincosf per CTA, shared by all heads, and
+    // evaluated before the grid dependency resolves (positions were written many kernels ago).
     {
-      const float pos = (float)tl;
+      const int half_rot = p.rotary_dim >> 1;
+      if (tid < DH / 2 && tid < half_rot) {
+        const float inv_freq = ((float)tl * p.rope_scale) / powf(p.rope_base, (float)(2 * tid) / (float)p.rotary_dim);
+        sincosf(inv_freq, &rope_sn[tid], &rope_cs[tid]);
+      }
+    }
+    pdl_wait();  // q, k, v are the previous kernel's output
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    {
       const int half_rot = p.rotary_dim >> 1;
       for (int item = tid; item < 9 * (DH / 2); item += 128) {
         const int h = item / (DH / 2), d = item - h * (DH / 2);
@@ -303,9 +313,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
                                     : p.k + (size_t)b * p.k_bs + (size_t)hkv * DH;
         __half* dst = (h < 8) ? q_s[h] : kv_new[0];
         if (d < half_rot) {
-          const float inv_freq = (pos * p.rope_scale) / powf(p.rope_base, (float)(2 * d) / (float)p.rotary_dim);
-          float sn, cs;
-          sincosf(inv_freq, &sn, &cs);
+          const float sn = rope_sn[d], cs = rope_cs[d];
           const float x = __half2float(src[d]), y = __half2float(src[d + half_rot]);
           dst[d] = __float2half_rn(cs * x - sn * y);
           dst[d + half_rot] = __float2half_rn(cs * y + sn * x);

@@ -47,7 +47,7 @@ struct Cfg {
   static constexpr int TMEM_A_BASE = ACC_BUFS * BN;  // columns
   static constexpr int TMEM_COLS = 512;
   static constexpr int OUT_PITCH = BM + 8;            // halves
-  static constexpr int STAGING = (BN * OUT_PITCH * 2 > BN * BM * 4) ? BN * OUT_PITCH * 2 : BN * BM * 4;
+  static constexpr int STAGING = (BN * OUT_PITCH * 2 > (BN + 8) * BM * 4) ? BN * OUT_PITCH * 2 : (BN + 8) * BM * 4;
   static constexpr int SMEM_B = 0;
   static constexpr int SMEM_W = SMEM_B + STAGES * B_STAGE;
   static constexpr int SMEM_S2 = SMEM_W + STAGES * W_STAGE;
@@ -74,7 +74,8 @@ struct GemmParams {
   int32_t* counters;        // [grid]
   int M, N, K, ldc;
   int n_tiles, m_tiles, kb_per_tile;
-  int mode;                 // 0 = DP, 1 = SK
+  int mode;                 // 0 = DP tiles, 1 = stream-K (L2 bulk-reduce), 2 = cluster split-K (DSMEM reduce-scatter)
+  int cluster_k;            // mode 2: CTAs per tile
   int units_per_cta;        // SK: K-blocks per CTA
   int group_m;              // DP raster: m-tiles per L2 group
   int dbg;                  // timing experiments only (OB_GEMM_DBG): 1 = no wait::st, 2 = no unpack, 4 = no MMA
@@ -90,7 +91,14 @@ struct SegIter {
     mode = p.mode;
     KB = p.kb_per_tile;
     total_tiles = p.n_tiles * p.m_tiles;
-    if (mode == 0) {
+    if (mode == 2) {
+      // one segment: tile = cluster index, K-range = rank-th slice of the tile's K-blocks
+      const int k = p.cluster_k, r = (int)cluster_ctarank();
+      tile = (int)cluster_id_x();
+      pos = (int)(((long long)KB * r) / k);
+      end = (int)(((long long)KB * (r + 1)) / k);
+      step = 0;
+    } else if (mode == 0) {
       tile = blockIdx.x;
       step = gridDim.x;
     } else {
@@ -102,6 +110,12 @@ struct SegIter {
     }
   }
   OB_DEVICE bool next(Seg& s) {
+    if (mode == 2) {
+      if (step) return false;
+      step = 1;
+      s.tile = tile; s.kb0 = pos; s.kb1 = end;
+      return end > pos;
+    }
     if (mode == 0) {
       if (tile >= total_tiles) return false;
       s.tile = tile;
@@ -201,9 +215,9 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.mode == 2) cluster_barrier();  // all CTAs of the cluster are running before any DSMEM store targets them
   const uint32_t tmem_base = *tmem_slot;
 
-  const int k32_per_row = p.K / 32;
 
   if (warp == 0) {
     // ================================================================ weight producer
@@ -333,13 +347,14 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     int acc = 0, acc_phase = 0;
     __half* stage16 = reinterpret_cast<__half*>(sStage);
     int32_t* stage32 = reinterpret_cast<int32_t*>(sStage);
+    bool cluster_done = false;
     pdl_wait();  // ascales / a_ssums come from the previous kernel; `out` may still be read by it
     while (it.next(sg)) {
       int nt, mt;
       tile_coords(p, sg.tile, nt, mt);
       const int m0 = mt * BN;
       const int n_row = nt * BM + q * 32 + lane;
-      const bool full_tile = (sg.kb0 == 0 && sg.kb1 == p.kb_per_tile);
+      const bool full_tile = (sg.kb0 == 0 && sg.kb1 == p.kb_per_tile) && p.mode != 2;
       const bool n_ok = n_row < p.N;
       float wsc = 0.f, wsz = 0.f;
       if (n_ok) {
@@ -374,6 +389,28 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
             stage16[(c0 + j) * C::OUT_PITCH + q * 32 + lane] = __float2half_rn(o);
           }
         }
+      } else if (p.mode == 2) {
+        // cluster split-K: reduce-scatter of the INT32 partials over distributed shared memory.  Rank o owns the
+        // token columns [o*cp, (o+1)*cp); every CTA deposits its partial for those columns in slot [its rank] of
+        // o's staging buffer (st.shared::cluster), exact and order independent.
+        const int k = p.cluster_k, my = (int)cluster_ctarank();
+        const int cp = (BN + k - 1) / k;
+        const uint32_t base_local = smem_u32(stage32);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_acc + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = c0 + j;
+            const int owner = col / cp;
+            const int lc = col - owner * cp;
+            const uint32_t off = (uint32_t)(((my * cp + lc) * BM + q * 32 + lane) * 4);
+            if (owner == my) stage32[(my * cp + lc) * BM + q * 32 + lane] = (int)r[j];
+            else st_shared_cluster_u32(mapa_shared(base_local + off, (uint32_t)owner), r[j]);
+          }
+        }
       } else {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -401,6 +438,26 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
               const uint4 v = *reinterpret_cast<const uint4*>(stage16 + row * C::OUT_PITCH + chunk * 8);
               *reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldc + n_base) = v;
             }
+          }
+        }
+      } else if (p.mode == 2) {
+        const int k = p.cluster_k, my = (int)cluster_ctarank();
+        const int cp = (BN + k - 1) / k;
+        cluster_barrier();  // every partial of this tile has landed in its owner's shared memory
+        cluster_done = true;
+        const int ncols = min(cp, BN - my * cp);
+        const int row = q * 32 + lane;
+        for (int lc = 0; lc < ncols; ++lc) {
+          int sum = 0;
+          for (int src = 0; src < k; ++src) sum += stage32[(src * cp + lc) * BM + row];
+          const int col = my * cp + lc;
+          const int m = m0 + col;
+          if (m < p.M && n_ok) {
+            const float ps = __int2float_rn(sum);
+            float o;
+            if (PER_GROUP) o = ps * (wsc * sTok[col]);
+            else o = __fmaf_rn(-wsz, sTok[BN + col], (ps * wsc) * sTok[col]);
+            p.out[(size_t)m * p.ldc + n_row] = __float2half_rn(o);
           }
         }
       } else {
@@ -454,7 +511,9 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // staging + sTok free for the next segment
     }
+    if (p.mode == 2 && !cluster_done) cluster_barrier();
   }
+  if (p.mode == 2 && warp < 8) cluster_barrier();  // non-epilogue warps: every thread of the cluster arrives once
 
   tc_fence_before();
   __syncthreads();
@@ -549,7 +608,8 @@ static int ensure_workspace(int dev, int sms) {
 }
 
 template <int BN, bool PG>
-static int launch(const CUtensorMap& map, const CUtensorMap& wmap, GemmParams& p, int grid, cudaStream_t st) {
+static int launch(const CUtensorMap& map, const CUtensorMap& wmap, GemmParams& p, int grid, unsigned cluster,
+                  cudaStream_t st) {
   using C = Cfg<BN>;
   auto kern = w4a8_gemm_kernel<BN, PG>;
   static bool attr_done = false;
@@ -558,7 +618,7 @@ static int launch(const CUtensorMap& map, const CUtensorMap& wmap, GemmParams& p
       return OB_ERR_CUDA;
     attr_done = true;
   }
-  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, map, wmap, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
+  return launch_pdl_cluster(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, cluster, map, wmap, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
 int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
@@ -586,8 +646,35 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   p.kb_per_tile = a.K / BK;
   const long long tiles = (long long)p.n_tiles * p.m_tiles;
   int grid;
-  const bool sk = a.force_mode >= 0 ? (a.force_mode == 1) : (tiles < 8LL * sms);
-  if (sk) {
+  unsigned cluster = 1;
+  // Scheduling choice (cost model in K-block times, constants from tools/gemm_micro.py: the L2 bulk-reduce finalisation
+  // of stream-K costs ~20 K-block times, a cluster DSMEM reduce ~3):
+  //   few tiles      -> cluster split-K: k CTAs per tile (k <= 8, tiles*k <= #SMs), reduce-scatter over DSMEM
+  //   medium         -> whichever of data-parallel tiles / stream-K is cheaper
+  //   many tiles     -> data-parallel tiles
+  int mode = a.force_mode;
+  const int KB = p.kb_per_tile;
+  int k_cl = (int)std::min<long long>(8, sms / std::max<long long>(1, tiles));
+  k_cl = std::min(k_cl, KB / 2);
+  if (mode < 0) {
+    if (k_cl >= 2) mode = 2;
+    else if (tiles >= 8LL * sms) mode = 0;
+    else {
+      const long long cost_dp = ((tiles + sms - 1) / sms) * KB;
+      const long long cost_sk = (tiles * KB + sms - 1) / sms + 20;
+      mode = cost_sk < cost_dp ? 1 : 0;
+    }
+  }
+  if (mode == 2 && k_cl < 2) mode = 1;
+  if (a.force_ctas > 0 && mode == 2) k_cl = std::max(2, std::min(k_cl, a.force_ctas));
+  p.cluster_k = 1;
+  if (mode == 2) {
+    p.mode = 2;
+    p.cluster_k = k_cl;
+    p.units_per_cta = KB;
+    cluster = (unsigned)k_cl;
+    grid = (int)tiles * k_cl;
+  } else if (mode == 1) {
     p.mode = 1;
     const long long total = tiles * p.kb_per_tile;
     p.units_per_cta = (int)((total + sms - 1) / sms);
@@ -604,7 +691,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   if (int e = make_w_map(&wmap, a.qweight, a.N, a.K)) return e;
 #define OB_LAUNCH(bn)                                                              \
   case bn:                                                                         \
-    return per_group ? launch<bn, true>(map, wmap, p, grid, st) : launch<bn, false>(map, wmap, p, grid, st);
+    return per_group ? launch<bn, true>(map, wmap, p, grid, cluster, st) : launch<bn, false>(map, wmap, p, grid, cluster, st);
   switch (BN) {
     OB_LAUNCH(16)
     OB_LAUNCH(32)

@@ -71,6 +71,13 @@ def test_forced_scheduling_modes_agree():
         run(96, 512, 1024, True, seed=9, bn=bn, mode=mode, ctas=ctas)
 
 
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 8])
+def test_cluster_split_k_dsmem_reduce(k):
+    """mode 2: k CTAs per tile, INT32 partials reduce-scattered over distributed shared memory (exact)."""
+    for (M, N, K, pg) in [(64, 512, 4096, False), (17, 256, 2048, True), (128, 384, 1024, False), (100, 128, 14336, False)]:
+        run(M, N, K, pg, seed=k * 7 + M, mode=2, ctas=k)
+
+
 def test_row_slice_output_view_and_n_multiple_of_32():
     run(40, 160, 256, False, seed=3, ldc=256)   # N = 160: last 128-row tile is partial (N % 32 == 0)
     run(40, 96, 256, True, seed=4, ldc=128)
