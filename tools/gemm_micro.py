@@ -55,6 +55,14 @@ if __name__ == "__main__" and os.environ.get("OB_GEMM_DBG"):
     sys.exit(0)
 
 if __name__ == "__main__":
+    run(64, 4096, 4096, tag="o_proj auto (cluster)")
+    run(64, 6144, 4096, tag="qkv auto (cluster)")
+    run(64, 28672, 4096, tag="gate_up auto")
+    run(64, 4096, 14336, tag="down auto (cluster)")
+    run(64, 4096, 4096, mode=2, ctas=2, tag="o_proj cluster k=2")
+    run(64, 4096, 4096, mode=2, ctas=8, tag="o_proj cluster k=8")
+    run(64, 4096, 14336, mode=2, ctas=8, tag="down cluster k=8")
+    run(16, 4096, 4096, tag="o_proj M=16 auto")
     run(64, 18944, 128, mode=0, tag="fixed cost (148 tiles,1kb)")
     run(64, 18944, 1024, mode=0, tag="148 tiles x 8 kb, no split")
     run(64, 18944, 4096, mode=0, tag="148 tiles x 32 kb, no split")
