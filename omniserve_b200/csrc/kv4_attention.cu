@@ -203,6 +203,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
   __shared__ __align__(16) __half kv_new[2][DH];
   __shared__ float qsum_s[8], qbias_s[8], cur_logit_s[8];
   __shared__ float rope_cs[DH / 2], rope_sn[DH / 2];
+  __shared__ int64_t kptr_s[32], vptr_s[32];
   __shared__ float ml_s[4][8][2];
   __shared__ __align__(8) uint64_t full[V2_STAGES], empty[V2_STAGES];
   __shared__ int flag_s;
@@ -265,27 +266,38 @@ kv4_decode_kernel(const AttnParams p, const int G) {
 
   if (warp == 4) {
     // ================================================================ producer (starts before the prologue)
-    if (lane == 0) {
-      int s = 0, ph = 0;
-      for (int v = v0; v < v1; ++v) {
-        // Pages older than the newest one were written at least two decode steps ago and are streamed while the
-        // previous kernel (the qkv GEMM) is still draining; the newest page holds the token appended by the
-        // previous step's attention call, so it is fetched only after the grid dependency resolved.
-        if (v == vis.n - 1) pdl_wait();
-        mbar_wait(&empty[s], ph ^ 1);
-        const Visit vv = vis.get(v);
-        const uint8_t* kp = reinterpret_cast<const uint8_t*>(sv.ktab[vv.tab]);
-        const uint8_t* vp = reinterpret_cast<const uint8_t*>(sv.vtab[vv.tab]);
-        uint8_t* st = ring + s * V2_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[s], V2_STAGE_BYTES);
-        bulk_g2s(st, kp + (size_t)sv.rank * 4096, 4096, &full[s]);
-        bulk_g2s(st + 4096, vp + (size_t)sv.rank * 4096, 4096, &full[s]);
-        bulk_g2s(st + 8192, kp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
-        bulk_g2s(st + 8192 + 128, kp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
-        bulk_g2s(st + 8192 + 256, vp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
-        bulk_g2s(st + 8192 + 384, vp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
-        if (++s == V2_STAGES) { s = 0; ph ^= 1; }
+    // Page pointers are fetched 32 visits at a time by the whole warp into shared memory so that the single
+    // issuing lane never waits on a dependent global load between bulk copies.
+    int s = 0, ph = 0;
+    for (int vb = v0; vb < v1; vb += 32) {
+      const int nv = min(32, v1 - vb);
+      if (lane < nv) {
+        const Visit vv = vis.get(vb + lane);
+        kptr_s[lane] = sv.ktab[vv.tab];
+        vptr_s[lane] = sv.vtab[vv.tab];
       }
+      __syncwarp();
+      if (lane == 0) {
+        for (int i = 0; i < nv; ++i) {
+          // Pages older than the newest one were written at least two decode steps ago and are streamed while the
+          // previous kernel (the qkv GEMM) is still draining; the newest page holds the token appended by the
+          // previous step's attention call, so it is fetched only after the grid dependency resolved.
+          if (vb + i == vis.n - 1) pdl_wait();
+          mbar_wait(&empty[s], ph ^ 1);
+          const uint8_t* kp = reinterpret_cast<const uint8_t*>(kptr_s[i]);
+          const uint8_t* vp = reinterpret_cast<const uint8_t*>(vptr_s[i]);
+          uint8_t* st = ring + s * V2_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], V2_STAGE_BYTES);
+          bulk_g2s(st, kp + (size_t)sv.rank * 4096, 4096, &full[s]);
+          bulk_g2s(st + 4096, vp + (size_t)sv.rank * 4096, 4096, &full[s]);
+          bulk_g2s(st + 8192, kp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
+          bulk_g2s(st + 8192 + 128, kp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
+          bulk_g2s(st + 8192 + 256, vp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
+          bulk_g2s(st + 8192 + 384, vp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
+          if (++s == V2_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ prologue: q/k RoPE, append new K/V

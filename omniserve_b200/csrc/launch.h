@@ -4,6 +4,7 @@
 // next kernel in; pdl_wait() must precede the first access to anything the previous kernel produced.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 namespace ob {
 
@@ -19,17 +20,22 @@ inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.numAttrs = 1;
+  int n = 0;
+  static const bool no_pdl = getenv("OB_NO_PDL") != nullptr;  // debugging aid
+  if (!no_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
   if (cluster_x > 1) {
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = cluster_x;
-    attr[1].val.clusterDim.y = 1;
-    attr[1].val.clusterDim.z = 1;
-    cfg.numAttrs = 2;
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
   }
   cfg.attrs = attr;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

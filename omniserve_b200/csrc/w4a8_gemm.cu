@@ -215,7 +215,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (p.mode == 2) cluster_barrier();  // all CTAs of the cluster are running before any DSMEM store targets them
+  if (p.mode == 2 && !(p.dbg & 16)) cluster_barrier();  // all CTAs of the cluster run before any DSMEM store targets them
   const uint32_t tmem_base = *tmem_slot;
 
 
@@ -407,7 +407,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
             const int owner = col / cp;
             const int lc = col - owner * cp;
             const uint32_t off = (uint32_t)(((my * cp + lc) * BM + q * 32 + lane) * 4);
-            if (owner == my) stage32[(my * cp + lc) * BM + q * 32 + lane] = (int)r[j];
+            if (owner == my || (p.dbg & 8)) stage32[(my * cp + lc) * BM + q * 32 + lane] = (int)r[j];
             else st_shared_cluster_u32(mapa_shared(base_local + off, (uint32_t)owner), r[j]);
           }
         }
@@ -630,7 +630,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!g_num_sms) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  const int sms = a.force_ctas > 0 ? std::min(a.force_ctas, g_num_sms) : g_num_sms;
+  const int sms = (a.force_ctas > 0 && a.force_mode != 2) ? std::min(a.force_ctas, g_num_sms) : g_num_sms;
   if (int e = ensure_workspace(dev, g_num_sms)) return e;
 
   int BN = a.M <= 16 ? 16 : a.M <= 32 ? 32 : a.M <= 64 ? 64 : 128;
@@ -654,19 +654,19 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   //   many tiles     -> data-parallel tiles
   int mode = a.force_mode;
   const int KB = p.kb_per_tile;
-  int k_cl = (int)std::min<long long>(8, sms / std::max<long long>(1, tiles));
-  k_cl = std::min(k_cl, KB / 2);
+  // cluster split-K (mode 2) measured no faster than stream-K on B200 for the Llama decode shapes (launch, first-byte
+  // and epilogue latencies dominate both), so it is opt-in: force_mode = 2, force_ctas = CTAs per tile.
+  int k_cl = a.force_mode == 2 ? (a.force_ctas > 0 ? a.force_ctas : 4) : 1;
+  k_cl = std::max(1, std::min(std::min(k_cl, 8), KB));
+  if (mode == 2 && k_cl < 2) mode = 1;
   if (mode < 0) {
-    if (k_cl >= 2) mode = 2;
-    else if (tiles >= 8LL * sms) mode = 0;
+    if (tiles >= 8LL * sms) mode = 0;
     else {
       const long long cost_dp = ((tiles + sms - 1) / sms) * KB;
       const long long cost_sk = (tiles * KB + sms - 1) / sms + 20;
       mode = cost_sk < cost_dp ? 1 : 0;
     }
   }
-  if (mode == 2 && k_cl < 2) mode = 1;
-  if (a.force_ctas > 0 && mode == 2) k_cl = std::max(2, std::min(k_cl, a.force_ctas));
   p.cluster_k = 1;
   if (mode == 2) {
     p.mode = 2;

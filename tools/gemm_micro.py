@@ -47,6 +47,12 @@ def run(M, N, K, mode=-1, bn=0, ctas=0, tag=""):
           f"{by / us / 1e3:8.1f} GB/s  {2.0 * M * N * K / us / 1e6:8.1f} TOPS", flush=True)
 
 
+if __name__ == "__main__" and os.environ.get("OB_CLUSTER_EXP"):
+    print("cluster experiment: OB_GEMM_DBG=%s OB_NO_PDL=%s" % (os.environ.get("OB_GEMM_DBG"), os.environ.get("OB_NO_PDL")))
+    for k in (2, 4):
+        run(64, 4096, 4096, mode=2, ctas=k, tag=f"o_proj cluster k={k}")
+    sys.exit(0)
+
 if __name__ == "__main__" and os.environ.get("OB_GEMM_DBG"):
     print("OB_GEMM_DBG =", os.environ["OB_GEMM_DBG"], "(results invalid, timing only)")
     run(64, 18944, 4096, mode=0, tag="148 tiles x 32 kb, no split")
