@@ -338,7 +338,9 @@ kv4_decode_kernel(const AttnParams p, const int G) {
       for (int d = tid; d < DH; d += 128) kv_new[1][d] = p.v[(size_t)b * p.v_bs + (size_t)hkv * DH + d];
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int h = warp; h < 8; h += 4) {
+    if (tid < 8) { qsum_s[tid] = 0.f; qbias_s[tid] = 0.f; cur_logit_s[tid] = -1.0e30f; }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int h = warp; h < G; h += 4) {
       // Full-precision logit of the new token (Template.hpp:1356-1376, log2 domain), then re-encode q for the
       // biased-nibble MMAs: odd dims are stored as q/16 because their nibbles enter as 1024 + 16 n.
       float s = 0.f, dot = 0.f, bias = 0.f;
@@ -722,7 +724,9 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
   const int ctas_y = per_q ? a.Hq : a.Hkv;
   const int base_ctas = a.B * ctas_y;
   int n_split = 1;
-  while (base_ctas * n_split < 6 * g_att_sms && max_pages / (n_split + 1) >= 4 && n_split < 64) ++n_split;
+  const int slots = 4 * g_att_sms;  // 4 CTAs of 160 threads are resident per SM
+  if (base_ctas * 5 < slots * 4)   // otherwise one CTA per (sequence, kv head) already fills >= 80 % of the machine
+    while (base_ctas * n_split < slots && max_pages / (n_split + 1) >= 4 && n_split < 64) ++n_split;
   if (a.force_split > 0) n_split = a.force_split;
   p.n_split = n_split;
   if (n_split > 1) {

@@ -1,0 +1,165 @@
+"""-m gpu: LServe masks of the decode attention: static streaming heads (sink + local ring
+pages) and dynamic page selection, against the oracle with the reference's index semantics
+(.../fused_attention_fine_grained/sparse_attention/decoderMaskedMultiheadAttentionTemplate.hpp:1559-1598,1631-1655;
+ring mapping common/kvCacheUtils.h:117-126)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.gpu_util import qkv_views, t
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+
+
+def _ring(blk, sink_blk, local_blk):
+    return blk if blk < sink_blk else sink_blk + (blk - sink_blk) % local_blk
+
+
+def _fill_stream(cache, table, L, sink_blk, local_blk, rng):
+    """Write tokens 0..L-1 of every head in order through the ring mapping (older local pages get overwritten)."""
+    from oracle import kv4
+    k = rng.standard_normal((L, cache.H, cache.Dh)).astype(np.float16)
+    v = rng.standard_normal((L, cache.H, cache.Dh)).astype(np.float16)
+    qk, sk, zk = kv4.kv4_quant(k)
+    qv, sv, zv = kv4.kv4_quant(v)
+    for pos in range(L):
+        page, slot = int(table[_ring(pos >> 6, sink_blk, local_blk)]), pos & 63
+        cache.data("k", page)[:, slot, :] = kv4.pack_nibbles(qk[pos]); cache.scales("k", page)[:, slot] = sk[pos]; cache.zeros("k", page)[:, slot] = zk[pos]
+        cache.data("v", page)[:, slot, :] = kv4.pack_nibbles(qv[pos]); cache.scales("v", page)[:, slot] = sv[pos]; cache.zeros("v", page)[:, slot] = zv[pos]
+
+
+def _ptrs(cache, tables):
+    kpool, vpool = t(cache.k_pool), t(cache.v_pool)
+    B, P = tables.shape
+    p = np.zeros((B, 2, P), np.int64)
+    p[:, 0] = kpool.data_ptr() + tables * cache.k_page_bytes
+    p[:, 1] = vpool.data_ptr() + tables * cache.v_page_bytes
+    return kpool, vpool, t(p)
+
+
+@pytest.mark.parametrize("lens", [(500, 130), (40, 1000), (385, 386)])
+def test_streaming_heads_sink_plus_local_ring(lens):
+    from omniserve_b200.backend import fused_attention_fine_grained_dense as op
+    from oracle import kv4
+    rng = np.random.default_rng(sum(lens))
+    B, Hq, Hkv, Dh = len(lens), 8, 2, 128
+    sink, local, sink_blk, local_blk = 128, 256, 2, 5
+    P = sink_blk + local_blk
+    cache = kv4.PagedKV4(B * P, Hkv, Dh)
+    tables = rng.permutation(B * P).reshape(B, P)
+    maxblk = (max(lens) >> 6) + 1
+    virt = np.zeros((B, maxblk), np.int64)   # logical block -> physical page through the ring
+    for b, L in enumerate(lens):
+        _fill_stream(cache, tables[b], L - 1, sink_blk, local_blk, rng)
+        for blk in range(maxblk):
+            virt[b, blk] = tables[b, _ring(blk, sink_blk, local_blk)]
+    q = rng.standard_normal((B, Hq, Dh)).astype(np.float16)
+    k = rng.standard_normal((B, Hkv, Dh)).astype(np.float16)
+    v = rng.standard_normal((B, Hkv, Dh)).astype(np.float16)
+    kpool, vpool, ptrs = _ptrs(cache, tables)
+    _, tq, tk, tv = qkv_views(q, k, v)
+    flags = t(np.zeros(Hkv, np.int32))           # every kv head is a streaming head
+    rank = t(np.arange(Hkv, dtype=np.int32))
+    out = op.single_query_attention(tq, tk, tv, None, ptrs, flags, rank, t(np.asarray(lens, np.int32)), None, 2048, 64,
+                                    0, Hkv * Dh // 2, sink, local, sink_blk, local_blk, 0, Hkv, max(lens) - 1, 128,
+                                    500000.0, 1.0, True, True, True, 2048)
+    torch.cuda.synchronize()
+
+    def positions(b, hq, tl):
+        n_valid = min(sink + local - 1, tl)
+        gap = tl - n_valid
+        return np.array([i if i < sink else i + gap for i in range(n_valid)], dtype=np.int64)
+    ref = kv4.decode_attention(q, k, v, cache, virt, lens, 128, 500000.0, mimic=False, positions_fn=positions).astype(np.float32)
+    got = out.cpu().numpy().astype(np.float32)
+    assert np.abs(got - ref).max() <= TOL * np.abs(ref).max()
+    np.testing.assert_array_equal(kpool.cpu().numpy(), cache.k_pool)   # append went through the ring mapping
+    np.testing.assert_array_equal(vpool.cpu().numpy(), cache.v_pool)
+
+
+@pytest.mark.parametrize("lens,P", [((700, 300), 4), ((1281, 1025), 9), ((64, 65), 1)])
+def test_dynamic_page_selection(lens, P):
+    from omniserve_b200.backend import fused_attention_fine_grained_sparse as op
+    from oracle import kv4
+    from tests.gpu_util import device_tables, make_kv_case
+    B, Hq, Hkv = len(lens), 8, 2
+    cache, bt, q, k, v = make_kv_case(B, Hq, Hkv, lens, seed=P * 100 + sum(lens))
+    rng = np.random.default_rng(P)
+    dyn = np.zeros((B, Hq, P), np.int32)
+    for b, L in enumerate(lens):
+        newest = (L - 2) // 64 if L >= 2 else 0     # page of the last cached token
+        for h in range(Hq):
+            others = rng.permutation(max(newest, 1))[: P - 1] if newest > 0 else np.zeros(P - 1, np.int64)
+            if len(others) < P - 1:
+                others = np.resize(others, P - 1)
+            dyn[b, h, : P - 1] = others
+            dyn[b, h, P - 1] = newest
+    kpool, vpool, ptrs = device_tables(cache, bt)
+    _, tq, tk, tv = qkv_views(q, k, v)
+    flags = t(np.ones(Hkv, np.int32))
+    rank = t(np.arange(Hkv, dtype=np.int32))
+    out = op.single_query_attention(tq, tk, tv, ptrs, None, flags, rank, t(dyn), t(np.asarray(lens, np.int32)), None, 4096,
+                                    64, Hkv * 64, 0, 0, 0, 0, 0, Hkv, 0, max(lens) - 1, 128, 500000.0, 1.0, True, True, True,
+                                    16, Hkv * 128, 2048)
+    torch.cuda.synchronize()
+
+    def positions(b, hq, tl):
+        if tl <= 0:
+            return np.zeros(0, np.int64)
+        pos = []
+        for j in range(P):
+            n = 64 if j < P - 1 else (tl - 1) % 64 + 1
+            pos.extend(range(int(dyn[b, hq, j]) * 64, int(dyn[b, hq, j]) * 64 + n))
+        return np.asarray(pos, np.int64)
+    ref = kv4.decode_attention(q, k, v, cache, bt, lens, 128, 500000.0, mimic=False, positions_fn=positions).astype(np.float32)
+    got = out.cpu().numpy().astype(np.float32)
+    assert np.abs(got - ref).max() <= TOL * np.abs(ref).max()
+    np.testing.assert_array_equal(kpool.cpu().numpy(), cache.k_pool)
+
+
+def test_mixed_retrieval_and_streaming_heads_with_rank_table():
+    from omniserve_b200.backend import fused_attention_fine_grained_dense as op
+    from oracle import kv4
+    from tests.gpu_util import device_tables, make_kv_case
+    lens = (450, 300)
+    B, Hq, Hkv, Dh = 2, 8, 4, 128
+    sink, local, sink_blk, local_blk = 64, 128, 1, 3
+    flags_np = np.array([1, 0, 0, 1], np.int32)      # kv heads 0,3 retrieval (ranks 0,1); 1,2 streaming (ranks 0,1)
+    rank_np = np.array([0, 0, 1, 1], np.int32)
+    rng = np.random.default_rng(77)
+    # retrieval pool: 2 heads
+    rc, rbt, q, _, _ = make_kv_case(B, Hq, 2, lens, seed=5)
+    Ps = sink_blk + local_blk
+    sc = kv4.PagedKV4(B * Ps, 2, Dh)
+    stab = rng.permutation(B * Ps).reshape(B, Ps)
+    maxblk = (max(lens) >> 6) + 1
+    virt = np.zeros((B, maxblk), np.int64)
+    for b, L in enumerate(lens):
+        _fill_stream(sc, stab[b], L - 1, sink_blk, local_blk, rng)
+        for blk in range(maxblk):
+            virt[b, blk] = stab[b, _ring(blk, sink_blk, local_blk)]
+    k = rng.standard_normal((B, Hkv, Dh)).astype(np.float16)
+    v = rng.standard_normal((B, Hkv, Dh)).astype(np.float16)
+    rk, rv, rptrs = device_tables(rc, rbt)
+    sk, sv_, sptrs = _ptrs(sc, stab)
+    _, tq, tk, tv = qkv_views(q, k, v)
+    out = op.single_query_attention(tq, tk, tv, rptrs, sptrs, t(flags_np), t(rank_np), t(np.asarray(lens, np.int32)), None,
+                                    2048, 64, 2 * 64, 2 * 64, sink, local, sink_blk, local_blk, 2, 2, max(lens) - 1, 128,
+                                    500000.0, 1.0, True, True, True, 2048)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.float32)
+
+    def spos(b, hq, tl):
+        n_valid = min(sink + local - 1, tl)
+        gap = tl - n_valid
+        return np.array([i if i < sink else i + gap for i in range(n_valid)], dtype=np.int64)
+    # oracle per pool: feed the pool's own two kv heads (+ their 2 query heads each)
+    g = Hq // Hkv
+    for pool_heads, cache, table, pf in (([0, 3], rc, rbt, None), ([1, 2], sc, virt, spos)):
+        qh = np.concatenate([q[:, h * g:(h + 1) * g] for h in pool_heads], axis=1)
+        ref = kv4.decode_attention(qh, k[:, pool_heads], v[:, pool_heads], cache, table, lens, 128, 500000.0, mimic=False,
+                                   positions_fn=pf).astype(np.float32)
+        mine = np.concatenate([got[:, h * g:(h + 1) * g] for h in pool_heads], axis=1)
+        assert np.abs(mine - ref).max() <= TOL * np.abs(ref).max()
+    np.testing.assert_array_equal(rk.cpu().numpy(), rc.k_pool)
+    np.testing.assert_array_equal(sk.cpu().numpy(), sc.k_pool)
