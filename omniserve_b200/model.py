@@ -203,6 +203,38 @@ class LlamaW4A8:
         self._flags = torch.ones(self.hkv, dtype=torch.int32, device=device)
         self._rank = torch.arange(self.hkv, dtype=torch.int32, device=device)
 
+    # ------------------------------------------------------------------ tensor-parallel sharding of a full model
+    def load_shard_of(self, full: "LlamaW4A8"):
+        """Overwrite this rank's parameters with its shard of `full` (a tp_size == 1 model on the same device):
+        qkv_proj / gate_up_proj column-parallel, o_proj / down_proj row-parallel on the K/32 tile axis (tp.py)."""
+        from . import tp
+        cfg, r, n = self.cfg, self.tp_rank, self.tp_size
+
+        def params(lin):
+            d = {"qweight": lin.qweight, "s1_scales": lin.s1_scales}
+            for k in ("s1_szeros", "s2_scales", "s2_zeros"):
+                if hasattr(lin, k):
+                    d[k] = getattr(lin, k)
+            return d
+
+        def assign(lin, d):
+            for k, v in d.items():
+                getattr(lin, k).copy_(v)
+
+        qkv_r = tp.qkv_ranges(cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, r, n)
+        gu_r = tp.gate_up_ranges(cfg.intermediate_size, r, n)
+        qs, it = full.q_size // n, cfg.intermediate_size // n
+        for mine, src in zip(self.layers, full.layers):
+            assign(mine["qkv_proj"], tp.shard_column(params(src["qkv_proj"]), qkv_r))
+            assign(mine["gate_up_proj"], tp.shard_column(params(src["gate_up_proj"]), gu_r))
+            assign(mine["o_proj"], tp.shard_row(params(src["o_proj"]), range(r * qs, (r + 1) * qs)))
+            assign(mine["down_proj"], tp.shard_row(params(src["down_proj"]), range(r * it, (r + 1) * it)))
+            mine["input_layernorm"].copy_(src["input_layernorm"])
+            mine["post_attention_layernorm"].copy_(src["post_attention_layernorm"])
+        self.norm_weight.copy_(full.norm_weight)
+        self.embed_tokens.copy_(full.embed_tokens)
+        self.lm_head.copy_(full.lm_head[r * self.vocab_local:(r + 1) * self.vocab_local])
+
     # ------------------------------------------------------------------ memory
     def weight_bytes(self) -> int:
         n = 0
