@@ -99,6 +99,11 @@ typedef struct ob_kv4_decode_args {
   int timestep;                                       /* max cached tokens over the batch */
   int rotary_embedding_dim; float rotary_base; float rotary_scale; /* scale = linear factor (1 = none) */
   int force_split;                                    /* 0 = auto */
+  /* fused_attention_fine_grained_sparse only (sparse_attention/...Template.hpp:1414-1429): when
+   * tokens_per_sub_chunk > 0 the K append of a retrieval head also folds the new post-RoPE key into the page's
+   * kmax / kmin statistics of its sub-chunk (element-wise max / min with what is stored there). */
+  int tokens_per_sub_chunk;
+  int hidden_dim_per_retrieval_token;                 /* num_retrieval_kv_heads * head_dim */
 } ob_kv4_decode_args;
 int ob_kv4_single_query_attention(const ob_kv4_decode_args* args, void* stream);
 
@@ -120,6 +125,35 @@ int ob_kv4_apply_rope_update_kv_cache(const ob_kv4_prefill_args* args, void* str
 
 /* ---- compute_padding_offsets (common/input_metadata_helper.cu:16-49) */
 int ob_compute_padding_offsets(int32_t* out, const int32_t* cu_seqlens, int batch, int max_seqlen, void* stream);
+
+/* ---- fused_attention_ctx_pool.paged_min_max_pool (sparse_utils/ContextPool/context_pool_kernel.cu:145-213)
+ * keys: fp16 [T, H_in, 128] post-RoPE (row / head strides in elements); for every sequence b, pooled head j
+ * (input head pooling_heads_idx[j]) and `pooling_size`-token sub-chunk, the channel-wise max / min over the
+ * sub-chunk's valid tokens is written to the kmax / kmin area of the K page that holds the sub-chunk. */
+int ob_paged_min_max_pool(const void* keys, const int64_t* retrieval_kv_pointers, const int32_t* cu_seqlens,
+                          const int32_t* pooling_heads_idx, long long row_stride, long long head_stride,
+                          int r_max_pages, int batch, int num_pooling_heads, int head_dim, int max_seqlen,
+                          int pooling_size, int page_size, int size_per_retrieval_token, int kv_cache_with_zeros,
+                          void* stream);
+
+/* ---- fused_attention_selector.single_query_page_selector
+ * (sparse_utils/KVPageSelector/fused_kv_page_selector.cpp:171-334, KVPageSelectorTemplate.hpp:786-1290)
+ * out: fp16 [B, Hq, padded] with padded = roundup(ceil(timestep / tokens_per_sub_chunk), sub-chunks per page);
+ * zeroed by this call, rows of streaming heads stay zero.  score[sub] = sum_d max(q_d*kmax_d, q_d*kmin_d)
+ * with q rotated to position length-1, fp16 arithmetic as in the reference. */
+typedef struct ob_page_selector_args {
+  const void* q; long long q_batch_stride;            /* fp16 [B,Hq,128] view, head stride 128 */
+  void* out;
+  const int64_t* retrieval_kv_pointers; int r_max_pages;
+  const int32_t* length_per_sample;                   /* [B] incl. the new token, or NULL (= timestep + 1) */
+  const int32_t* retrieval_head_flags; const int32_t* head_rank_table;   /* [Hkv] or NULL */
+  int batch, num_heads, num_kv_heads, head_dim, tokens_per_block;
+  int size_per_retrieval_token, num_retrieval_kv_heads;
+  int timestep;
+  int rotary_embedding_dim; float rotary_base; float rotary_scale;
+  int tokens_per_sub_chunk, hidden_dim_per_retrieval_token;
+} ob_page_selector_args;
+int ob_kv4_page_selector(const ob_page_selector_args* args, void* stream);
 
 #ifdef __cplusplus
 }

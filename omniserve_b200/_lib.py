@@ -35,6 +35,7 @@ class KV4DecodeArgs(C.Structure):
         ("timestep", c_i),
         ("rotary_embedding_dim", c_i), ("rotary_base", c_f), ("rotary_scale", c_f),
         ("force_split", c_i),
+        ("tokens_per_sub_chunk", c_i), ("hidden_dim_per_retrieval_token", c_i),
     ]
 
 
@@ -48,6 +49,19 @@ class KV4PrefillArgs(C.Structure):
         ("num_retrieval_kv_heads", c_i), ("num_streaming_kv_heads", c_i),
         ("sink_token_num", c_i), ("local_token_num", c_i), ("sink_block_num", c_i), ("local_block_num", c_i),
         ("rotary_embedding_dim", c_i), ("rotary_base", c_f), ("rotary_scale", c_f),
+    ]
+
+
+class PageSelectorArgs(C.Structure):
+    _fields_ = [
+        ("q", c_p), ("q_batch_stride", c_ll), ("out", c_p),
+        ("retrieval_kv_pointers", c_p), ("r_max_pages", c_i),
+        ("length_per_sample", c_p), ("retrieval_head_flags", c_p), ("head_rank_table", c_p),
+        ("batch", c_i), ("num_heads", c_i), ("num_kv_heads", c_i), ("head_dim", c_i), ("tokens_per_block", c_i),
+        ("size_per_retrieval_token", c_i), ("num_retrieval_kv_heads", c_i),
+        ("timestep", c_i),
+        ("rotary_embedding_dim", c_i), ("rotary_base", c_f), ("rotary_scale", c_f),
+        ("tokens_per_sub_chunk", c_i), ("hidden_dim_per_retrieval_token", c_i),
     ]
 
 
@@ -70,13 +84,9 @@ _SIGS = {
     "ob_kv4_single_query_attention": ([C.POINTER(KV4DecodeArgs), c_p], c_i),
     "ob_kv4_apply_rope_update_kv_cache": ([C.POINTER(KV4PrefillArgs), c_p], c_i),
     "ob_compute_padding_offsets": ([c_p] * 2 + [c_i] * 2 + [c_p], c_i),
+    "ob_paged_min_max_pool": ([c_p] * 4 + [c_ll] * 2 + [c_i] * 9 + [c_p], c_i),
+    "ob_kv4_page_selector": ([C.POINTER(PageSelectorArgs), c_p], c_i),
 }
-# optional (later rows of SURVEY section 8): present once lserve_ops.cu is built
-_OPTIONAL_SIGS = {
-    "ob_paged_min_max_pool": ([c_p] * 5 + [c_i] * 8 + [c_p], c_i),
-    "ob_kv4_page_selector": None,
-}
-
 EXPORTS = tuple(_SIGS)
 
 

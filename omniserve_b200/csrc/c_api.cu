@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/omniserve_b200.h.
 #include "../../include/omniserve_b200.h"
 #include "kv4_attention.h"
+#include "lserve_ops.h"
 #include "small_ops.h"
 #include "w4a8_gemm.h"
 
@@ -132,6 +133,8 @@ int ob_kv4_single_query_attention(const ob_kv4_decode_args* x, void* stream) {
   a.rotary_dim = x->rotary_embedding_dim; a.rotary_base = x->rotary_base;
   a.rotary_scale = x->rotary_scale != 0.f ? 1.0f / x->rotary_scale : 1.0f;
   a.force_split = x->force_split;
+  a.tokens_per_sub_chunk = x->tokens_per_sub_chunk;
+  a.hidden_dim_per_retrieval_token = x->hidden_dim_per_retrieval_token;
   return kv4_decode_run(a, ST(stream));
 }
 
@@ -154,6 +157,40 @@ int ob_kv4_apply_rope_update_kv_cache(const ob_kv4_prefill_args* x, void* stream
 int ob_compute_padding_offsets(int32_t* out, const int32_t* cu_seqlens, int batch, int max_seqlen, void* stream) {
   if (!out || !cu_seqlens) return OB_ERR_ARG;
   return padding_offsets_run(out, cu_seqlens, batch, max_seqlen, ST(stream));
+}
+
+int ob_paged_min_max_pool(const void* keys, const int64_t* retrieval_kv_pointers, const int32_t* cu_seqlens,
+                          const int32_t* pooling_heads_idx, long long row_stride, long long head_stride,
+                          int r_max_pages, int batch, int num_pooling_heads, int head_dim, int max_seqlen,
+                          int pooling_size, int page_size, int size_per_retrieval_token, int kv_cache_with_zeros,
+                          void* stream) {
+  if (!keys || !retrieval_kv_pointers || !cu_seqlens || !pooling_heads_idx) return OB_ERR_ARG;
+  PoolArgs a{};
+  a.keys = H(keys); a.row_stride = row_stride; a.head_stride = head_stride;
+  a.retrieval_kv_pointers = retrieval_kv_pointers; a.r_max_pages = r_max_pages;
+  a.cu_seqlens = cu_seqlens; a.pooling_heads_idx = pooling_heads_idx;
+  a.batch = batch; a.num_pooling_heads = num_pooling_heads; a.head_dim = head_dim;
+  a.max_seqlen = max_seqlen; a.pooling_size = pooling_size; a.page_size = page_size;
+  a.size_per_retrieval_token = size_per_retrieval_token; a.kv_cache_with_zeros = kv_cache_with_zeros;
+  return paged_min_max_pool_run(a, ST(stream));
+}
+
+int ob_kv4_page_selector(const ob_page_selector_args* x, void* stream) {
+  if (!x || !x->q || !x->out || !x->retrieval_kv_pointers) return OB_ERR_ARG;
+  SelectorArgs a{};
+  a.q = H(x->q); a.q_bs = x->q_batch_stride; a.out = HM(x->out);
+  a.retrieval_kv_pointers = x->retrieval_kv_pointers; a.r_max_pages = x->r_max_pages;
+  a.lengths = x->length_per_sample;
+  a.retrieval_head_flags = x->retrieval_head_flags; a.head_rank_table = x->head_rank_table;
+  a.B = x->batch; a.Hq = x->num_heads; a.Hkv = x->num_kv_heads; a.head_dim = x->head_dim;
+  a.tokens_per_block = x->tokens_per_block;
+  a.size_per_retrieval_token = x->size_per_retrieval_token; a.num_retrieval_kv_heads = x->num_retrieval_kv_heads;
+  a.timestep = x->timestep;
+  a.rotary_dim = x->rotary_embedding_dim; a.rotary_base = x->rotary_base;
+  a.rotary_scale = x->rotary_scale != 0.f ? 1.0f / x->rotary_scale : 1.0f;
+  a.tokens_per_sub_chunk = x->tokens_per_sub_chunk;
+  a.hidden_dim_per_retrieval_token = x->hidden_dim_per_retrieval_token;
+  return page_selector_run(a, ST(stream));
 }
 
 }  // extern "C"

@@ -119,6 +119,7 @@ struct AttnParams {
   int n_split;
   float* part_o; float* part_ml; int* counters;         // split-KV workspace
   int timestep;                                         // used when lengths == null
+  int sub_chunk, eles_per_ind;                          // LServe page statistics (sparse op): 0 = none
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -381,6 +382,23 @@ kv4_decode_kernel(const AttnParams p, const int G) {
       for (int i = 0; i < 4; ++i) x[i] = kv_new[which][lane * 4 + i];
       __half* sc = reinterpret_cast<__half*>(page + sv.data_bytes) + sv.rank * TPB + slot;
       quant_store_token(x, page + (size_t)sv.rank * TPB * (DH / 2) + slot * (DH / 2), sc, sc + sv.hpool * TPB, lane);
+      if (which == 0 && is_retrieval && p.sub_chunk > 0) {
+        // LServe: fold the appended post-RoPE key into the kmax / kmin statistics of its sub-chunk, element-wise
+        // against what the page holds (sparse_attention/...Template.hpp:1414-1429; fmaxf / fminf on fp16 values).
+        __half* stats = reinterpret_cast<__half*>(page + sv.data_bytes) + 2 * sv.hpool * TPB;
+        __half* mxp = stats + (size_t)(slot / p.sub_chunk) * p.eles_per_ind + sv.rank * DH + lane * 4;
+        __half* mnp = mxp + (size_t)(TPB / p.sub_chunk) * p.eles_per_ind;
+        uint2 a = *reinterpret_cast<const uint2*>(mxp), c = *reinterpret_cast<const uint2*>(mnp);
+        __half* ah = reinterpret_cast<__half*>(&a);
+        __half* ch = reinterpret_cast<__half*>(&c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ah[i] = __float2half_rn(fmaxf(__half2float(ah[i]), __half2float(x[i])));
+          ch[i] = __float2half_rn(fminf(__half2float(ch[i]), __half2float(x[i])));
+        }
+        *reinterpret_cast<uint2*>(mxp) = a;
+        *reinterpret_cast<uint2*>(mnp) = c;
+      }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
@@ -718,6 +736,8 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
   p.local_blk = a.local_blocks > 0 ? a.local_blocks : 1;
   p.rope_base = a.rotary_base; p.rope_scale = a.rotary_scale; p.rotary_dim = a.rotary_dim;
   p.timestep = a.timestep;
+  p.sub_chunk = a.tokens_per_sub_chunk; p.eles_per_ind = a.hidden_dim_per_retrieval_token;
+  if (p.sub_chunk < 0 || (p.sub_chunk > 0 && TPB % p.sub_chunk)) return OB_ERR_SHAPE;
 
   // KV splits: enough CTAs to balance 148 SMs x ~4 resident CTAs, at least 4 pages per split
   const int max_pages = std::max(1, (std::max(1, a.max_attended) + TPB - 1) / TPB);

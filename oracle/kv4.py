@@ -233,7 +233,7 @@ def _qk_cached_mimic(q_r: np.ndarray, kd: np.ndarray) -> np.ndarray:
 
 def decode_attention(q, k, v, cache: PagedKV4, block_table, lengths, rotary_dim: int, base: float,
                      scale: float = 1.0, mimic: bool = True, positions_fn=None, head_rank=None,
-                     append: bool = True):
+                     append: bool = True, update_stats_sub_chunk: int = 0):
     """``single_query_attention`` of fused_attention_pure_dense (and, through ``positions_fn`` /
     ``head_rank``, the LServe masked variants).
 
@@ -247,6 +247,9 @@ def decode_attention(q, k, v, cache: PagedKV4, block_table, lengths, rotary_dim:
 
     positions_fn(b, hq, tl) -> int array of *cached* token positions to attend (default: all 0..tl-1);
     head_rank[hkv] -> row of that kv head inside the page (default: identity).
+    update_stats_sub_chunk > 0 (fused_attention_fine_grained_sparse, retrieval heads): the appended post-RoPE key
+    is folded into the page's kmax / kmin of its sub-chunk, element-wise against the stored values
+    (sparse_attention/decoderMaskedMultiheadAttentionTemplate.hpp:1414-1429).
     """
     q = np.asarray(q, f16)
     k = np.asarray(k, f16)
@@ -310,20 +313,34 @@ def decode_attention(q, k, v, cache: PagedKV4, block_table, lengths, rotary_dim:
                 rank = hk if head_rank is None else int(head_rank[hk])
                 write_token(cache, "k", page, slot, rank, k_r[hk])
                 write_token(cache, "v", page, slot, rank, v[b, hk])
+                if update_stats_sub_chunk:
+                    kmax, kmin = cache.kstats(page)
+                    sub = slot // update_stats_sub_chunk
+                    sl = slice(rank * Dh, (rank + 1) * Dh)
+                    kmax[sub, sl] = np.maximum(kmax[sub, sl], k_r[hk])
+                    kmin[sub, sl] = np.minimum(kmin[sub, sl], k_r[hk])
     return out
 
 
 # ----------------------------------------------------------------------------------------------
-# LServe pieces (page statistics + selector score)
+# LServe pieces (page statistics, selector score, top-k page choice)
 # ----------------------------------------------------------------------------------------------
-def paged_min_max_pool(cache: PagedKV4, block_table, keys_post_rope_f16, seq_lens, sub_chunk: int = 16):
-    """paged_min_max_pool (sparse_utils/ContextPool/context_pool_kernel.cu:44-69): per 16-token
-    sub-chunk channel-wise max/min of post-RoPE K written after the scales/zeros of each K page."""
+def paged_min_max_pool(cache: PagedKV4, block_table, keys_post_rope_f16, seq_lens, sub_chunk: int = 16,
+                       pooling_heads_idx=None):
+    """paged_min_max_pool (sparse_utils/ContextPool/context_pool_kernel.cu:16-69): per ``sub_chunk``-token
+    sub-chunk channel-wise max/min of post-RoPE K written after the scales/zeros of each K page.
+    keys: fp16 [T, H_in, Dh] (sequences packed back to back); pooled head j reads input head
+    ``pooling_heads_idx[j]`` (default identity) and writes row j of the statistics (:31,:45).  A partial last
+    sub-chunk pools its valid tokens only (the clamp of :39 repeats the last token)."""
     t0 = 0
     n_sub = TOKENS_PER_BLOCK // sub_chunk
     assert cache.n_sub == n_sub
+    idx = np.arange(cache.H) if pooling_heads_idx is None else np.asarray(pooling_heads_idx)
+    assert len(idx) == cache.H
+    keys = np.asarray(keys_post_rope_f16, f16)
+    keys = keys.reshape(keys.shape[0], -1, cache.Dh)
     for b, L in enumerate(seq_lens):
-        kk = np.asarray(keys_post_rope_f16[t0 : t0 + L], f16).reshape(L, cache.H * cache.Dh)
+        kk = keys[t0 : t0 + L][:, idx, :].reshape(L, cache.H * cache.Dh)
         for c0 in range(0, L, sub_chunk):
             page = int(block_table[b, c0 // TOKENS_PER_BLOCK])
             sub = (c0 % TOKENS_PER_BLOCK) // sub_chunk
@@ -334,16 +351,83 @@ def paged_min_max_pool(cache: PagedKV4, block_table, keys_post_rope_f16, seq_len
         t0 += L
 
 
-def page_selector_scores(q_rope_f16, cache: PagedKV4, block_row, n_pages: int, head_rank: int):
-    """single_query_page_selector score (KVPageSelectorTemplate.hpp:478-503):
-    score[sub] = sum_d max(q_d*kmax_d, q_d*kmin_d); evaluated here in float64 (reference: fp16)."""
-    qd = np.asarray(q_rope_f16, f16).astype(f64)
-    Dh = cache.Dh
-    out = np.zeros((n_pages, cache.n_sub), f64)
-    for p in range(n_pages):
-        kmax, kmin = cache.kstats(int(block_row[p]))
-        for s in range(cache.n_sub):
-            a = kmax[s, head_rank * Dh : (head_rank + 1) * Dh].astype(f64) * qd
-            bb = kmin[s, head_rank * Dh : (head_rank + 1) * Dh].astype(f64) * qd
-            out[p, s] = np.maximum(a, bb).sum()
-    return out
+def _score_fp16(q_r: np.ndarray, kmax: np.ndarray, kmin: np.ndarray) -> np.ndarray:
+    """qk_hmma_dot_min_max<16> (KVPageSelectorTemplate.hpp:478-503) for rows kmax/kmin [n, Dh]:
+    16 lanes x 8 channels; per lane four half2 products rounded to fp16, ``__hmax2``, sequential fp16 ``__hadd2``
+    over the four pairs, ``__hadd`` of the two halves, then an fp32 butterfly (xor 8,4,2,1) across the 16 lanes."""
+    n = kmax.shape[0]
+    qq = q_r.astype(f32).reshape(1, 16, 4, 2)
+    a = (qq * kmax.astype(f32).reshape(n, 16, 4, 2)).astype(f16)    # fp16 x fp16 product is exact in fp32 -> one rounding
+    b = (qq * kmin.astype(f32).reshape(n, 16, 4, 2)).astype(f16)
+    m = np.maximum(a, b)
+    acc = m[:, :, 0, :]
+    for i in (1, 2, 3):
+        acc = (acc.astype(f32) + m[:, :, i, :].astype(f32)).astype(f16)
+    v = (acc[:, :, 0].astype(f32) + acc[:, :, 1].astype(f32)).astype(f16).astype(f32)   # [n, 16]
+    lanes = np.arange(16)
+    for msk in (8, 4, 2, 1):
+        v = (v + v[:, lanes ^ msk]).astype(f32)
+    return v[:, 0].astype(f16)
+
+
+def page_selector(q, cache: PagedKV4, block_table, lengths, timestep: int, rotary_dim: int, base: float,
+                  scale: float = 1.0, retrieval_flags=None, head_rank=None, n_kv_heads: int | None = None,
+                  sub_chunk: int = 16):
+    """single_query_page_selector (fused_kv_page_selector.cpp:171-334 + KVPageSelectorTemplate.hpp:786-1290).
+
+    q fp16 [B,Hq,Dh] pre-RoPE; lengths [B] incl. the new token (None -> timestep + 1).  Returns fp16
+    [B, Hq, padded(timestep)] zero-initialised (:274-277); retrieval heads get score[sub] for sub < ceil(tl/sub_chunk)
+    at row pitch ``padded(tl_b)`` -- the kernel derives the pitch from the sample's own length (:1130-1133), which
+    equals the host's only when lengths[b] == timestep + 1 (kept as is; writes past the tensor are dropped here).
+    Streaming heads are skipped (:791-794)."""
+    q = np.asarray(q, f16)
+    B, Hq, Dh = q.shape
+    Hkv = n_kv_heads if n_kv_heads is not None else (len(retrieval_flags) if retrieval_flags is not None else cache.H)
+    g = Hq // Hkv
+    grp = TOKENS_PER_BLOCK // sub_chunk
+    n_sub_host = (timestep + sub_chunk - 1) // sub_chunk
+    padded_host = (n_sub_host + grp - 1) // grp * grp
+    out = np.zeros(B * Hq * padded_host, f16)
+    for b in range(B):
+        tl = timestep if lengths is None else int(lengths[b]) - 1
+        n_sub = (tl + sub_chunk - 1) // sub_chunk
+        padded = (n_sub + grp - 1) // grp * grp
+        q_r = rope_neox(q[b], tl, rotary_dim, base, scale)
+        for hq in range(Hq):
+            hk = hq // g
+            if retrieval_flags is not None and not retrieval_flags[hk]:
+                continue
+            rank = hk if head_rank is None else int(head_rank[hk])
+            sl = slice(rank * Dh, (rank + 1) * Dh)
+            rows_max = np.empty((n_sub, Dh), f16)
+            rows_min = np.empty((n_sub, Dh), f16)
+            for sc in range(n_sub):
+                kmax, kmin = cache.kstats(int(block_table[b, sc // grp]))
+                rows_max[sc] = kmax[sc % grp, sl]
+                rows_min[sc] = kmin[sc % grp, sl]
+            sc_vals = _score_fp16(q_r[hq], rows_max, rows_min) if n_sub else np.zeros(0, f16)
+            o = (b * Hq + hq) * padded
+            hi = min(o + n_sub, out.size)
+            if hi > o:
+                out[o:hi] = sc_vals[: hi - o]
+    return out.reshape(B, Hq, padded_host)
+
+
+def select_topk_pages(stats, timestep: int, token_budget: int, sub_chunk: int = 16):
+    """The Python half of the selector (omniserve/modeling/layers/decoding_attention.py:88-143):
+    stats fp16 [B,Hq,padded] -> int32 [B,Hq,P]: max over the sub-chunks of a page, top-(k-1) over all pages but the
+    last (k = min(max(3, budget/64), pages)), the newest page appended last.  Ties are broken towards the lower
+    page index here (torch.topk's order among equal values is unspecified)."""
+    stats = np.asarray(stats)
+    B, Hq, padded = stats.shape
+    grp = TOKENS_PER_BLOCK // sub_chunk
+    if timestep <= token_budget:
+        n = timestep // TOKENS_PER_BLOCK + 1
+        return np.broadcast_to(np.arange(n, dtype=np.int32), (B, Hq, n)).copy()
+    budget = min(token_budget, timestep)
+    page_stats = stats.reshape(B, Hq, padded // grp, grp).astype(f32).max(axis=-1)
+    total = page_stats.shape[-1]
+    kk = min(max(3, budget // TOKENS_PER_BLOCK), total) - 1
+    order = np.argsort(-page_stats[:, :, :-1], axis=-1, kind="stable")[:, :, :kk]
+    last = np.full((B, Hq, 1), total - 1, np.int64)
+    return np.concatenate([order, last], axis=-1).astype(np.int32)

@@ -55,12 +55,12 @@ def make_gemm_inputs(M, N, K, seed, per_group=False):
     return d
 
 
-def make_kv_case(B, Hq, Hkv, lens, seed, extra_pages=2):
+def make_kv_case(B, Hq, Hkv, lens, seed, extra_pages=2, k_stats_subchunks=0):
     from oracle import kv4 as okv
     rng = np.random.default_rng(seed)
     Dh = 128
     n_pages = sum((l + 63) // 64 for l in lens) + extra_pages
-    cache = okv.PagedKV4(n_pages, Hkv, Dh)
+    cache = okv.PagedKV4(n_pages, Hkv, Dh, k_stats_subchunks)
     perm = rng.permutation(n_pages)
     max_pages = max((l + 63) // 64 for l in lens)
     bt = np.zeros((B, max_pages), np.int64)

@@ -83,8 +83,13 @@ def test_dynamic_page_selection(lens, P):
     from oracle import kv4
     from tests.gpu_util import device_tables, make_kv_case
     B, Hq, Hkv = len(lens), 8, 2
-    cache, bt, q, k, v = make_kv_case(B, Hq, Hkv, lens, seed=P * 100 + sum(lens))
+    # the sparse op also folds the appended key into the K pages' kmax / kmin statistics (4 sub-chunks of 16 tokens)
+    cache, bt, q, k, v = make_kv_case(B, Hq, Hkv, lens, seed=P * 100 + sum(lens), k_stats_subchunks=4)
     rng = np.random.default_rng(P)
+    for pg in range(cache.P):   # non-trivial stored statistics so that the max / min with the new key is exercised
+        kmax, kmin = cache.kstats(pg)
+        kmax[:] = rng.standard_normal(kmax.shape).astype(np.float16)
+        kmin[:] = rng.standard_normal(kmin.shape).astype(np.float16)
     dyn = np.zeros((B, Hq, P), np.int32)
     for b, L in enumerate(lens):
         newest = (L - 2) // 64 if L >= 2 else 0     # page of the last cached token
@@ -111,10 +116,12 @@ def test_dynamic_page_selection(lens, P):
             n = 64 if j < P - 1 else (tl - 1) % 64 + 1
             pos.extend(range(int(dyn[b, hq, j]) * 64, int(dyn[b, hq, j]) * 64 + n))
         return np.asarray(pos, np.int64)
-    ref = kv4.decode_attention(q, k, v, cache, bt, lens, 128, 500000.0, mimic=False, positions_fn=positions).astype(np.float32)
+    ref = kv4.decode_attention(q, k, v, cache, bt, lens, 128, 500000.0, mimic=False, positions_fn=positions,
+                               update_stats_sub_chunk=16).astype(np.float32)
     got = out.cpu().numpy().astype(np.float32)
     assert np.abs(got - ref).max() <= TOL * np.abs(ref).max()
-    np.testing.assert_array_equal(kpool.cpu().numpy(), cache.k_pool)
+    np.testing.assert_array_equal(kpool.cpu().numpy(), cache.k_pool)   # nibbles, scales, zeros AND kmax / kmin
+    np.testing.assert_array_equal(vpool.cpu().numpy(), cache.v_pool)
 
 
 def test_mixed_retrieval_and_streaming_heads_with_rank_table():
