@@ -40,24 +40,29 @@ constexpr int A_COLS_PER_STAGE = BK / 4;  // 32 TMEM columns hold 128 x 128 int8
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  // Three decoupled rings.  Packed weights come from HBM (long latency, nothing downstream holds them once they
+  // are unpacked): deep ring, released by the unpack warps.  Activations come from L2 and the unpacked INT8
+  // weights live in TMEM: shallow rings, released when the MMAs that read them retire.
+  static constexpr int W_STAGES = (BN >= 128) ? 10 : (BN >= 64 ? 14 : 16);
+  static constexpr int B_STAGES = (BN >= 128) ? 4 : 6;
+  static constexpr int A_SLOTS = 8;
   static constexpr int B_STAGE = BN * BK;
   static constexpr int S2_STAGE = 256;
-  static constexpr int ACC_BUFS = (BN >= 256) ? 1 : 2;
+  static constexpr int ACC_BUFS = 2;
   static constexpr int TMEM_A_BASE = ACC_BUFS * BN;  // columns
   static constexpr int TMEM_COLS = 512;
   static constexpr int OUT_PITCH = BM + 8;            // halves
   static constexpr int STAGING = (BN * OUT_PITCH * 2 > (BN + 8) * BM * 4) ? BN * OUT_PITCH * 2 : (BN + 8) * BM * 4;
   static constexpr int SMEM_B = 0;
-  static constexpr int SMEM_W = SMEM_B + STAGES * B_STAGE;
-  static constexpr int SMEM_S2 = SMEM_W + STAGES * W_STAGE;
-  static constexpr int SMEM_STAGING = SMEM_S2 + STAGES * S2_STAGE;
+  static constexpr int SMEM_W = SMEM_B + B_STAGES * B_STAGE;
+  static constexpr int SMEM_S2 = SMEM_W + W_STAGES * W_STAGE;
+  static constexpr int SMEM_STAGING = SMEM_S2 + W_STAGES * S2_STAGE;
   static constexpr int SMEM_TOK = SMEM_STAGING + STAGING;      // float sa[BN], ss[BN]
   static constexpr int SMEM_BAR = SMEM_TOK + BN * 8;
-  static constexpr int NUM_BARS = 3 * STAGES + 2 * ACC_BUFS;
+  static constexpr int NUM_BARS = 2 * W_STAGES + 2 * B_STAGES + 2 * A_SLOTS + 2 * ACC_BUFS;
   static constexpr int SMEM_MISC = SMEM_BAR + NUM_BARS * 8;    // tmem slot, flags
   static constexpr int SMEM_TOTAL = SMEM_MISC + 64 + 1024;      // + alignment slack
-  static_assert(TMEM_A_BASE + STAGES * A_COLS_PER_STAGE <= 512, "TMEM budget");
+  static_assert(TMEM_A_BASE + A_SLOTS * A_COLS_PER_STAGE <= 512, "TMEM budget");
   static_assert(SMEM_TOTAL <= 227 * 1024, "smem budget");
 };
 
@@ -78,6 +83,7 @@ struct GemmParams {
   int cluster_k;            // mode 2: CTAs per tile
   int units_per_cta;        // SK: K-blocks per CTA
   int group_m;              // DP raster: m-tiles per L2 group
+  int w_rows2k;             // weight tensor map variant: 4 rows of 2 KB per K-block instead of 16 rows of 512 B
   int dbg;                  // timing experiments only (OB_GEMM_DBG): 1 = no wait::st, 2 = no unpack, 4 = no MMA
 };
 
@@ -185,10 +191,13 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
   uint8_t* sStage = smem + C::SMEM_STAGING;
   float* sTok = reinterpret_cast<float*>(smem + C::SMEM_TOK);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SMEM_BAR);
-  uint64_t* full = bars;                       // TMA landed (B + packed W [+ s2])
-  uint64_t* empty = bars + C::STAGES;          // MMAs that read stage s finished
-  uint64_t* a_full = bars + 2 * C::STAGES;     // unpack warps filled the TMEM A slot
-  uint64_t* acc_full = bars + 3 * C::STAGES;
+  uint64_t* w_full = bars;                               // packed weights (+ s2) landed
+  uint64_t* w_empty = w_full + C::W_STAGES;               // unpack warps read the stage into registers
+  uint64_t* b_full = w_empty + C::W_STAGES;               // activation tile landed
+  uint64_t* b_empty = b_full + C::B_STAGES;               // MMAs that read the tile retired
+  uint64_t* a_full = b_empty + C::B_STAGES;               // unpack warps filled the TMEM A slot
+  uint64_t* a_empty = a_full + C::A_SLOTS;                // MMAs that read the slot retired
+  uint64_t* acc_full = a_empty + C::A_SLOTS;
   uint64_t* acc_empty = acc_full + C::ACC_BUFS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::SMEM_MISC);
   int* sFlag = reinterpret_cast<int*>(smem + C::SMEM_MISC + 8);
@@ -200,11 +209,9 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&act_map);
     tma_prefetch_desc(&w_map);
-    for (int i = 0; i < C::STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-      mbar_init(&a_full[i], 4);
-    }
+    for (int i = 0; i < C::W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 4); }
+    for (int i = 0; i < C::B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < C::A_SLOTS; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::ACC_BUFS; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);
@@ -229,15 +236,18 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       it.init(p);
       int stage = 0, phase = 0;
       while (it.next(p)) {
-        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_wait(&w_empty[stage], phase ^ 1);
         const int n_cnt = min(BM, p.N - it.nt * BM);
-        mbar_arrive_expect_tx(&full[stage], C::B_STAGE + W_STAGE + (PER_GROUP ? 2 * n_cnt : 0));
-        tma_load_3d(sW + stage * W_STAGE, &w_map, 0, it.kb * 4, it.nt * 4, &full[stage]);
-        if (PER_GROUP) {
-          bulk_g2s(sS2 + stage * C::S2_STAGE, p.s2_scales + (size_t)it.kb * p.N + it.nt * BM, n_cnt, &full[stage]);
-          bulk_g2s(sS2 + stage * C::S2_STAGE + 128, p.s2_zeros + (size_t)it.kb * p.N + it.nt * BM, n_cnt, &full[stage]);
+        mbar_arrive_expect_tx(&w_full[stage], ((p.dbg & 64) ? 0 : W_STAGE) + (PER_GROUP ? 2 * n_cnt : 0));
+        if (!(p.dbg & 64)) {
+          if (p.w_rows2k) tma_load_3d(sW + stage * W_STAGE, &w_map, 0, it.kb, it.nt * 4, &w_full[stage]);
+          else tma_load_3d(sW + stage * W_STAGE, &w_map, 0, it.kb * 4, it.nt * 4, &w_full[stage]);
         }
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        if (PER_GROUP) {
+          bulk_g2s(sS2 + stage * C::S2_STAGE, p.s2_scales + (size_t)it.kb * p.N + it.nt * BM, n_cnt, &w_full[stage]);
+          bulk_g2s(sS2 + stage * C::S2_STAGE + 128, p.s2_zeros + (size_t)it.kb * p.N + it.nt * BM, n_cnt, &w_full[stage]);
+        }
+        if (++stage == C::W_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 3) {
@@ -249,9 +259,10 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       it.init(p);
       int stage = 0, phase = 0;
       while (it.next(p)) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, it.mt * BN, &full[stage]);
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        mbar_wait(&b_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&b_full[stage], (p.dbg & 32) ? 0 : C::B_STAGE);
+        if (!(p.dbg & 32)) tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, it.mt * BN, &b_full[stage]);
+        if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -259,29 +270,31 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     SegIter it;
     it.init(p);
     Seg sg;
-    int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    int bs = 0, bph = 0, as = 0, aph = 0, acc = 0, acc_phase = 0;
     constexpr uint32_t idesc = umma_idesc_i8(BM, BN, true, true);
     while (it.next(sg)) {
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
-        mbar_wait(&a_full[stage], phase);
+        mbar_wait(&b_full[bs], bph);
+        mbar_wait(&a_full[as], aph);
         tc_fence_after();
         if (lane == 0) {
-          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sB + stage * C::B_STAGE));
-          const uint32_t a_tmem = tmem_base + C::TMEM_A_BASE + stage * A_COLS_PER_STAGE;
+          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sB + bs * C::B_STAGE));
+          const uint32_t a_tmem = tmem_base + C::TMEM_A_BASE + as * A_COLS_PER_STAGE;
           if (!(p.dbg & 4)) {
 #pragma unroll
             for (int a = 0; a < 4; ++a)
               umma_i8_ts(d_tmem, a_tmem + a * 8, bdesc + (uint64_t)(a * 2), idesc, (kb > sg.kb0 || a > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          umma_commit(&b_empty[bs]);
+          umma_commit(&a_empty[as]);
           if (kb == sg.kb1 - 1) umma_commit(&acc_full[acc]);
         }
         __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
+        if (++as == C::A_SLOTS) { as = 0; aph ^= 1; }
       }
       if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1; }
     }
@@ -291,35 +304,40 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     SegIter it;
     it.init(p);
     Seg sg;
-    int stage = 0, phase = 0;
+    int ws = 0, wph = 0, as = 0, aph = 0;
     while (it.next(sg)) {
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
+        mbar_wait(&w_full[ws], wph);
+        mbar_wait(&a_empty[as], aph ^ 1);
+        tc_fence_after();
         if (p.dbg & 2) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[stage]);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (lane == 0) { mbar_arrive(&w_empty[ws]); mbar_arrive(&a_full[as]); }
+          if (++ws == C::W_STAGES) { ws = 0; wph ^= 1; }
+          if (++as == C::A_SLOTS) { as = 0; aph ^= 1; }
           continue;
         }
-        const uint8_t* wsm = sW + stage * W_STAGE + q * 2048 + lane * 16;
+        const uint8_t* wsm = sW + ws * W_STAGE + q * 2048 + lane * 16;
         uint32_t sc[4], zr[4];
         if (PER_GROUP) {
-          const uint32_t ps = *reinterpret_cast<const uint32_t*>(sS2 + stage * C::S2_STAGE + q * 32 + (lane >> 2) * 4);
-          const uint32_t pz = *reinterpret_cast<const uint32_t*>(sS2 + stage * C::S2_STAGE + 128 + q * 32 + (lane >> 2) * 4);
+          const uint32_t ps = *reinterpret_cast<const uint32_t*>(sS2 + ws * C::S2_STAGE + q * 32 + (lane >> 2) * 4);
+          const uint32_t pz = *reinterpret_cast<const uint32_t*>(sS2 + ws * C::S2_STAGE + 128 + q * 32 + (lane >> 2) * 4);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             sc[j] = (ps >> (8 * j)) & 0xFFu;
             zr[j] = ((pz >> (8 * j)) & 0xFFu) * 0x01010101u;
           }
         }
-        const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE + stage * A_COLS_PER_STAGE;
+        const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE + as * A_COLS_PER_STAGE;
         const uint32_t t_hi = t_lo + (16u << 16);
+        uint4 v[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) v[a] = *reinterpret_cast<const uint4*>(wsm + a * 512);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          const uint4 v = *reinterpret_cast<const uint4*>(wsm + a * 512);
-          uint32_t l0 = v.x & 0x0F0F0F0Fu, l1 = v.y & 0x0F0F0F0Fu, l2 = v.z & 0x0F0F0F0Fu, l3 = v.w & 0x0F0F0F0Fu;
-          uint32_t h0 = (v.x >> 4) & 0x0F0F0F0Fu, h1 = (v.y >> 4) & 0x0F0F0F0Fu, h2 = (v.z >> 4) & 0x0F0F0F0Fu,
-                   h3 = (v.w >> 4) & 0x0F0F0F0Fu;
+          uint32_t l0 = v[a].x & 0x0F0F0F0Fu, l1 = v[a].y & 0x0F0F0F0Fu, l2 = v[a].z & 0x0F0F0F0Fu, l3 = v[a].w & 0x0F0F0F0Fu;
+          uint32_t h0 = (v[a].x >> 4) & 0x0F0F0F0Fu, h1 = (v[a].y >> 4) & 0x0F0F0F0Fu, h2 = (v[a].z >> 4) & 0x0F0F0F0Fu,
+                   h3 = (v[a].w >> 4) & 0x0F0F0F0Fu;
           if (PER_GROUP) {
             // rows: l0,l2 -> c (scale 0); l1,l3 -> c+8 (scale 1); h0,h2 -> c+16 (scale 2); h1,h3 -> c+24 (scale 3)
             l0 = vadd4(l0 * sc[0], zr[0]); l2 = vadd4(l2 * sc[0], zr[0]);
@@ -330,11 +348,15 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
           tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
           tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
         }
+        // the packed stage is in registers: hand it back to the producer before waiting for the TMEM stores
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&w_empty[ws]);
         if (!(p.dbg & 1)) tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[stage]);
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive(&a_full[as]);
+        if (++ws == C::W_STAGES) { ws = 0; wph ^= 1; }
+        if (++as == C::A_SLOTS) { as = 0; aph ^= 1; }
       }
     }
   } else if (warp >= 8) {
@@ -481,29 +503,54 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (*sFlag) {
           __threadfence();
-          // finalize: elementwise over [BN tokens][128 n]; 8 consecutive n per item
-          for (int item = et; item < BN * 16; item += 128) {
-            const int row = item >> 4, chunk = item & 15;
-            const int m = m0 + row;
-            const int n_base = nt * BM + chunk * 8;
-            int4* src = reinterpret_cast<int4*>(slot + row * BM + chunk * 8);
-            int4 a0 = __ldcg(src), a1 = __ldcg(src + 1);
-            __stcg(src, make_int4(0, 0, 0, 0));
-            __stcg(src + 1, make_int4(0, 0, 0, 0));
-            if (m < p.M && n_base < p.N) {
-              const int av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-              const float sa = sTok[row], ss = sTok[BN + row];
-              __align__(16) __half o[8];
+          // finalize: elementwise over [BN tokens][128 n]; thread et owns the 8 columns n_base.. of rows
+          // (et >> 4) + 8 i.  All L2 reads of a batch are issued before anything depends on them (the slot was
+          // written by other SMs, so every read is an L2 round trip: batching turns BN/8 dependent trips into one).
+          const int chunk = et & 15;
+          const int n_base = nt * BM + chunk * 8;
+          const bool n_in = n_base < p.N;
+          float wsc8[8], wsz8[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float w = __half2float(p.wscales[n_base + j]);
-                const float ps = __int2float_rn(av[j]);
-                float r;
-                if (PER_GROUP) r = ps * (w * sa);
-                else r = __fmaf_rn(-__half2float(p.w_szs[n_base + j]), ss, (ps * w) * sa);
-                o[j] = __float2half_rn(r);
+          for (int j = 0; j < 8; ++j) {
+            wsc8[j] = n_in ? __half2float(p.wscales[n_base + j]) : 0.f;
+            wsz8[j] = (!PER_GROUP && n_in) ? __half2float(p.w_szs[n_base + j]) : 0.f;
+          }
+          constexpr int ROWS_PER_BATCH = 8;   // 8 rows x 2 int4 = 64 registers in flight
+#pragma unroll 1
+          for (int r0 = et >> 4; r0 < BN; r0 += 8 * ROWS_PER_BATCH) {
+            int4 a0[ROWS_PER_BATCH], a1[ROWS_PER_BATCH];
+#pragma unroll
+            for (int i = 0; i < ROWS_PER_BATCH; ++i) {
+              const int row = r0 + 8 * i;
+              if (row < BN) {
+                const int4* src = reinterpret_cast<const int4*>(slot + row * BM + chunk * 8);
+                a0[i] = __ldcg(src);
+                a1[i] = __ldcg(src + 1);
               }
-              *reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldc + n_base) = *reinterpret_cast<uint4*>(o);
+            }
+#pragma unroll
+            for (int i = 0; i < ROWS_PER_BATCH; ++i) {
+              const int row = r0 + 8 * i;
+              if (row < BN) {
+                int4* src = reinterpret_cast<int4*>(slot + row * BM + chunk * 8);
+                __stcg(src, make_int4(0, 0, 0, 0));
+                __stcg(src + 1, make_int4(0, 0, 0, 0));
+                const int m = m0 + row;
+                if (m < p.M && n_in) {
+                  const int av[8] = {a0[i].x, a0[i].y, a0[i].z, a0[i].w, a1[i].x, a1[i].y, a1[i].z, a1[i].w};
+                  const float sa = sTok[row], ss = sTok[BN + row];
+                  __align__(16) __half o[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float ps = __int2float_rn(av[j]);
+                    float r;
+                    if (PER_GROUP) r = ps * (wsc8[j] * sa);
+                    else r = __fmaf_rn(-wsz8[j], ss, (ps * wsc8[j]) * sa);
+                    o[j] = __float2half_rn(r);
+                  }
+                  *reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldc + n_base) = *reinterpret_cast<uint4*>(o);
+                }
+              }
             }
           }
           if (et == 0) p.counters[first_cta] = 0;
@@ -568,19 +615,21 @@ static int make_act_map(CUtensorMap* out, const void* ptr, int M, int K, int BN)
   return 0;
 }
 
-static int make_w_map(CUtensorMap* out, const void* ptr, int N, int K) {
+static int make_w_map(CUtensorMap* out, const void* ptr, int N, int K, bool rows2k) {
   static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
-  MapKey key{ptr, N, K, -1};
+  MapKey key{ptr, N, K, rows2k ? -2 : -1};
   auto f = cache.find(key);
   if (f != cache.end()) { *out = f->second; return 0; }
   PFN_encodeTiled enc = get_encode();
   if (!enc) return OB_ERR_DRIVER;
   // [N/32][K/32][512 B] as 8-byte elements: dims (fastest first) {64, K/32, N/32}
-  cuuint64_t dims[3] = {64, (cuuint64_t)(K / 32), (cuuint64_t)(N / 32)};
-  cuuint64_t strides[2] = {512, (cuuint64_t)(K / 32) * 512};
-  cuuint32_t box[3] = {64, 4, 4};
+  // rows2k: the 4 k32 blocks of a K-block are contiguous (2 KB), so the same bytes can be described as
+  // {256, K/128, N/32} with a {256, 1, 4} box: 4 rows of 2 KB instead of 16 rows of 512 B (same smem image).
+  cuuint64_t dims[3] = {rows2k ? 256u : 64u, (cuuint64_t)(rows2k ? K / 128 : K / 32), (cuuint64_t)(N / 32)};
+  cuuint64_t strides[2] = {rows2k ? 2048u : 512u, (cuuint64_t)(K / 32) * 512};
+  cuuint32_t box[3] = {rows2k ? 256u : 64u, rows2k ? 1u : 4u, 4};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -688,7 +737,8 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   CUtensorMap map;
   if (int e = make_act_map(&map, a.in_feats, a.M, a.K, BN)) return e;
   CUtensorMap wmap;
-  if (int e = make_w_map(&wmap, a.qweight, a.N, a.K)) return e;
+  { const char* e2 = getenv("OB_GEMM_W2K"); p.w_rows2k = (e2 && atoi(e2)) ? 1 : 0; }
+  if (int e = make_w_map(&wmap, a.qweight, a.N, a.K, p.w_rows2k != 0)) return e;
 #define OB_LAUNCH(bn)                                                              \
   case bn:                                                                         \
     return per_group ? launch<bn, true>(map, wmap, p, grid, cluster, st) : launch<bn, false>(map, wmap, p, grid, cluster, st);

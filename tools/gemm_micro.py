@@ -47,6 +47,23 @@ def run(M, N, K, mode=-1, bn=0, ctas=0, tag=""):
           f"{by / us / 1e3:8.1f} GB/s  {2.0 * M * N * K / us / 1e6:8.1f} TOPS", flush=True)
 
 
+if __name__ == "__main__" and os.environ.get("OB_STREAM_EXP"):
+    # what bounds the per-K-block time of the load pipeline?  (results invalid for dbg != 0: timing only)
+    for w2k in ("0", "1"):
+        os.environ["OB_GEMM_W2K"] = w2k
+        for dbg, what in ((0, "full"), (6, "no unpack, no MMA"), (6 + 32, "W only (no act TMA)"), (6 + 64, "act only (no W TMA)")):
+            os.environ["OB_GEMM_DBG"] = str(dbg)
+            for M in (64, 16):
+                run(M, 18944, 14336, mode=0, tag=f"w2k={w2k} {what} M={M}")
+            run(64, 4096, 14336, mode=0, tag=f"w2k={w2k} {what} 32 CTAs")
+    os.environ["OB_GEMM_DBG"] = "0"
+    for w2k in ("0", "1"):
+        os.environ["OB_GEMM_W2K"] = w2k
+        run(64, 28672, 4096, tag=f"gate_up auto w2k={w2k}")
+        run(64, 4096, 14336, tag=f"down auto w2k={w2k}")
+        run(8192, 6144, 4096, tag=f"prefill qkv w2k={w2k}")
+    sys.exit(0)
+
 if __name__ == "__main__" and os.environ.get("OB_CLUSTER_EXP"):
     print("cluster experiment: OB_GEMM_DBG=%s OB_NO_PDL=%s" % (os.environ.get("OB_GEMM_DBG"), os.environ.get("OB_NO_PDL")))
     for k in (2, 4):
