@@ -202,6 +202,16 @@ OB_DEVICE void cluster_barrier() {
 }
 
 // ------------------------------------------------------------------------------------------ misc
+OB_DEVICE uint4 lds_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+OB_DEVICE uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
 OB_DEVICE uint4 ld_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -43,8 +43,8 @@ struct Cfg {
   // Three decoupled rings.  Packed weights come from HBM (long latency, nothing downstream holds them once they
   // are unpacked): deep ring, released by the unpack warps.  Activations come from L2 and the unpacked INT8
   // weights live in TMEM: shallow rings, released when the MMAs that read them retire.
-  static constexpr int W_STAGES = (BN >= 128) ? 10 : (BN >= 64 ? 14 : 16);
-  static constexpr int B_STAGES = (BN >= 128) ? 4 : 6;
+  static constexpr int W_STAGES = (BN >= 128) ? 6 : (BN >= 64 ? 14 : 16);
+  static constexpr int B_STAGES = 6;
   static constexpr int A_SLOTS = 8;
   static constexpr int B_STAGE = BN * BK;
   static constexpr int S2_STAGE = 256;
@@ -304,35 +304,48 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     SegIter it;
     it.init(p);
     Seg sg;
-    int ws = 0, wph = 0, as = 0, aph = 0;
+    // Software pipelined: the TMEM stores of K-block i are only waited for (tcgen05.wait::st) while the packed
+    // bytes of K-block i+1 are already on their way from shared memory, so the store-completion latency is off the
+    // per-K-block critical path of this warp (it was ~half of it).  a_full(i) is therefore signalled one iteration
+    // late -- the 8-deep TMEM ring absorbs that -- and once more after the last K-block.
+    int ws = 0, wph = 0, as = 0, aph = 0, pending = -1;
+    const uint32_t sW_u32 = smem_u32(sW), sS2_u32 = smem_u32(sS2);
     while (it.next(sg)) {
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
         mbar_wait(&w_full[ws], wph);
-        mbar_wait(&a_empty[as], aph ^ 1);
-        tc_fence_after();
         if (p.dbg & 2) {
           __syncwarp();
-          if (lane == 0) { mbar_arrive(&w_empty[ws]); mbar_arrive(&a_full[as]); }
+          if (lane == 0) { mbar_arrive(&w_empty[ws]); }
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (lane == 0) { mbar_arrive(&a_full[as]); }
           if (++ws == C::W_STAGES) { ws = 0; wph ^= 1; }
           if (++as == C::A_SLOTS) { as = 0; aph ^= 1; }
           continue;
         }
-        const uint8_t* wsm = sW + ws * W_STAGE + q * 2048 + lane * 16;
+        const uint32_t wsm = sW_u32 + ws * W_STAGE + q * 2048 + lane * 16;
+        uint4 v[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) v[a] = lds_v4(wsm + a * 512);
         uint32_t sc[4], zr[4];
         if (PER_GROUP) {
-          const uint32_t ps = *reinterpret_cast<const uint32_t*>(sS2 + ws * C::S2_STAGE + q * 32 + (lane >> 2) * 4);
-          const uint32_t pz = *reinterpret_cast<const uint32_t*>(sS2 + ws * C::S2_STAGE + 128 + q * 32 + (lane >> 2) * 4);
+          const uint32_t ps = lds_u32(sS2_u32 + ws * C::S2_STAGE + q * 32 + (lane >> 2) * 4);
+          const uint32_t pz = lds_u32(sS2_u32 + ws * C::S2_STAGE + 128 + q * 32 + (lane >> 2) * 4);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             sc[j] = (ps >> (8 * j)) & 0xFFu;
             zr[j] = ((pz >> (8 * j)) & 0xFFu) * 0x01010101u;
           }
         }
+        if (pending >= 0) {   // previous K-block: its TMEM stores have had a whole iteration to land
+          if (!(p.dbg & 1)) tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[pending]);
+        }
+        mbar_wait(&a_empty[as], aph ^ 1);
+        tc_fence_after();
         const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE + as * A_COLS_PER_STAGE;
         const uint32_t t_hi = t_lo + (16u << 16);
-        uint4 v[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) v[a] = *reinterpret_cast<const uint4*>(wsm + a * 512);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
           uint32_t l0 = v[a].x & 0x0F0F0F0Fu, l1 = v[a].y & 0x0F0F0F0Fu, l2 = v[a].z & 0x0F0F0F0Fu, l3 = v[a].w & 0x0F0F0F0Fu;
@@ -348,16 +361,19 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
           tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
           tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
         }
-        // the packed stage is in registers: hand it back to the producer before waiting for the TMEM stores
+        // the packed stage is in registers: hand it back to the producer right away
         __syncwarp();
         if (lane == 0) mbar_arrive(&w_empty[ws]);
-        if (!(p.dbg & 1)) tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[as]);
+        pending = as;
         if (++ws == C::W_STAGES) { ws = 0; wph ^= 1; }
         if (++as == C::A_SLOTS) { as = 0; aph ^= 1; }
       }
+    }
+    if (pending >= 0) {
+      if (!(p.dbg & 1)) tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[pending]);
     }
   } else if (warp >= 8) {
     // ================================================================ epilogue
@@ -697,7 +713,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   int grid;
   unsigned cluster = 1;
   // Scheduling choice (cost model in K-block times, constants from tools/gemm_micro.py: the L2 bulk-reduce finalisation
-  // of stream-K costs ~20 K-block times, a cluster DSMEM reduce ~3):
+  // of stream-K costs ~12 K-block times):
   //   few tiles      -> cluster split-K: k CTAs per tile (k <= 8, tiles*k <= #SMs), reduce-scatter over DSMEM
   //   medium         -> whichever of data-parallel tiles / stream-K is cheaper
   //   many tiles     -> data-parallel tiles
@@ -712,7 +728,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     if (tiles >= 8LL * sms) mode = 0;
     else {
       const long long cost_dp = ((tiles + sms - 1) / sms) * KB;
-      const long long cost_sk = (tiles * KB + sms - 1) / sms + 20;
+      const long long cost_sk = (tiles * KB + sms - 1) / sms + 12;
       mode = cost_sk < cost_dp ? 1 : 0;
     }
   }

@@ -92,3 +92,17 @@ def qkv_views(q, k, v):
     qkv = torch.cat([t(q).reshape(B, -1), t(k).reshape(B, -1), t(v).reshape(B, -1)], dim=1).contiguous()
     return (qkv, qkv[:, :Hq * Dh].view(B, Hq, Dh), qkv[:, Hq * Dh:(Hq + Hkv) * Dh].view(B, Hkv, Dh),
             qkv[:, (Hq + Hkv) * Dh:].view(B, Hkv, Dh))
+
+
+def assert_k_pool_equal(got_pool, cache, max_stat_ulp=2, max_stat_frac=1e-3):
+    """K pages: nibbles, scales and zeros bit-exact; the kmax / kmin statistics (raw post-RoPE fp16 keys) may differ
+    from the numpy oracle in the last bits of a few elements (fp32 sincosf on the device vs numpy's libm)."""
+    got = got_pool.cpu().numpy() if hasattr(got_pool, "cpu") else got_pool
+    cut = cache.data_bytes + cache.sz_bytes
+    np.testing.assert_array_equal(got[:, :cut], cache.k_pool[:, :cut])
+    if cache.stats_bytes:
+        a = np.ascontiguousarray(got[:, cut:]).view(np.int16).astype(np.int32)
+        b = np.ascontiguousarray(cache.k_pool[:, cut:]).view(np.int16).astype(np.int32)
+        diff = np.abs(a - b)
+        assert diff.max() <= max_stat_ulp, f"statistics differ by {diff.max()} fp16 ulps"
+        assert (diff != 0).mean() <= max_stat_frac

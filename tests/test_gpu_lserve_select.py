@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.gpu_util import qkv_views, ref_module, t
+from tests.gpu_util import assert_k_pool_equal, qkv_views, ref_module, t
 
 pytestmark = pytest.mark.gpu
 
@@ -152,8 +152,11 @@ def test_dynamic_sparse_decode_loop_end_to_end():
                                    update_stats_sub_chunk=16).astype(np.float32)
         got = out.cpu().numpy().astype(np.float32)
         assert np.abs(got - ref).max() <= 2e-3 * np.abs(ref).max()
-        np.testing.assert_array_equal(kpool.cpu().numpy(), cache.k_pool)
+        assert_k_pool_equal(kpool, cache)
         np.testing.assert_array_equal(vpool.cpu().numpy(), cache.v_pool)
+        # keep the oracle's statistics in lock-step with the device's (they may differ in the last fp16 bit), so that
+        # a one-ulp difference cannot flip a later page choice
+        cache.k_pool[:] = kpool.cpu().numpy()
 
 
 def test_selector_full_size_properties():
