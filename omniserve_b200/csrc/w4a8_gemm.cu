@@ -43,9 +43,9 @@ struct Cfg {
   // Three decoupled rings.  Packed weights come from HBM (long latency, nothing downstream holds them once they
   // are unpacked): deep ring, released by the unpack warps.  Activations come from L2 and the unpacked INT8
   // weights live in TMEM: shallow rings, released when the MMAs that read them retire.
-  static constexpr int W_STAGES = (BN >= 128) ? 6 : (BN >= 64 ? 14 : 16);
-  static constexpr int B_STAGES = 6;
-  static constexpr int A_SLOTS = 8;
+  static constexpr int W_STAGES = (BN >= 128) ? 6 : (BN >= 64 ? 12 : 16);
+  static constexpr int B_STAGES = (BN >= 128) ? 6 : 8;   // activation ring and TMEM A ring advance in lock-step:
+  static constexpr int A_SLOTS = B_STAGES;                 // one tcgen05.commit per K-block frees both
   static constexpr int B_STAGE = BN * BK;
   static constexpr int S2_STAGE = 256;
   static constexpr int ACC_BUFS = 2;
@@ -59,7 +59,7 @@ struct Cfg {
   static constexpr int SMEM_STAGING = SMEM_S2 + W_STAGES * S2_STAGE;
   static constexpr int SMEM_TOK = SMEM_STAGING + STAGING;      // float sa[BN], ss[BN]
   static constexpr int SMEM_BAR = SMEM_TOK + BN * 8;
-  static constexpr int NUM_BARS = 2 * W_STAGES + 2 * B_STAGES + 2 * A_SLOTS + 2 * ACC_BUFS;
+  static constexpr int NUM_BARS = 2 * W_STAGES + 3 * B_STAGES + 2 * ACC_BUFS;
   static constexpr int SMEM_MISC = SMEM_BAR + NUM_BARS * 8;    // tmem slot, flags
   static constexpr int SMEM_TOTAL = SMEM_MISC + 64 + 1024;      // + alignment slack
   static_assert(TMEM_A_BASE + A_SLOTS * A_COLS_PER_STAGE <= 512, "TMEM budget");
@@ -194,10 +194,9 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
   uint64_t* w_full = bars;                               // packed weights (+ s2) landed
   uint64_t* w_empty = w_full + C::W_STAGES;               // unpack warps read the stage into registers
   uint64_t* b_full = w_empty + C::W_STAGES;               // activation tile landed
-  uint64_t* b_empty = b_full + C::B_STAGES;               // MMAs that read the tile retired
-  uint64_t* a_full = b_empty + C::B_STAGES;               // unpack warps filled the TMEM A slot
-  uint64_t* a_empty = a_full + C::A_SLOTS;                // MMAs that read the slot retired
-  uint64_t* acc_full = a_empty + C::A_SLOTS;
+  uint64_t* a_full = b_full + C::B_STAGES;                // unpack warps filled the TMEM A slot
+  uint64_t* ba_empty = a_full + C::B_STAGES;              // MMAs that read activation stage s / TMEM slot s retired
+  uint64_t* acc_full = ba_empty + C::B_STAGES;
   uint64_t* acc_empty = acc_full + C::ACC_BUFS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::SMEM_MISC);
   int* sFlag = reinterpret_cast<int*>(smem + C::SMEM_MISC + 8);
@@ -210,8 +209,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     tma_prefetch_desc(&act_map);
     tma_prefetch_desc(&w_map);
     for (int i = 0; i < C::W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 4); }
-    for (int i = 0; i < C::B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < C::A_SLOTS; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&a_full[i], 4); mbar_init(&ba_empty[i], 1); }
     for (int i = 0; i < C::ACC_BUFS; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);
@@ -259,7 +257,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       it.init(p);
       int stage = 0, phase = 0;
       while (it.next(p)) {
-        mbar_wait(&b_empty[stage], phase ^ 1);
+        mbar_wait(&ba_empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&b_full[stage], (p.dbg & 32) ? 0 : C::B_STAGE);
         if (!(p.dbg & 32)) tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, it.mt * BN, &b_full[stage]);
         if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
@@ -270,31 +268,35 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     SegIter it;
     it.init(p);
     Seg sg;
-    int bs = 0, bph = 0, as = 0, aph = 0, acc = 0, acc_phase = 0;
+    // The issue loop is the throughput limiter for narrow tiles (4 short MMAs per K-block), so it is kept lean:
+    // one elected lane (elect.sync lets ptxas use plain uniform-register moves instead of a waterfall loop),
+    // descriptors advanced by adds from loop-invariant bases, one commit per K-block.
+    int st = 0, ph = 0, acc = 0, acc_phase = 0;
     constexpr uint32_t idesc = umma_idesc_i8(BM, BN, true, true);
+    const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(sB));
+    const uint32_t a_tmem0 = tmem_base + C::TMEM_A_BASE;
     while (it.next(sg)) {
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-        mbar_wait(&b_full[bs], bph);
-        mbar_wait(&a_full[as], aph);
+        mbar_wait(&b_full[st], ph);
+        mbar_wait(&a_full[st], ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sB + bs * C::B_STAGE));
-          const uint32_t a_tmem = tmem_base + C::TMEM_A_BASE + as * A_COLS_PER_STAGE;
+        if (elect_one()) {
+          const uint64_t bdesc = bdesc0 + (uint64_t)((st * C::B_STAGE) >> 4);
+          const uint32_t a_tmem = a_tmem0 + st * A_COLS_PER_STAGE;
           if (!(p.dbg & 4)) {
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-              umma_i8_ts(d_tmem, a_tmem + a * 8, bdesc + (uint64_t)(a * 2), idesc, (kb > sg.kb0 || a > 0) ? 1u : 0u);
+            umma_i8_ts(d_tmem, a_tmem, bdesc, idesc, kb > sg.kb0 ? 1u : 0u);
+            umma_i8_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1u);
+            umma_i8_ts(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1u);
+            umma_i8_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1u);
           }
-          umma_commit(&b_empty[bs]);
-          umma_commit(&a_empty[as]);
+          umma_commit(&ba_empty[st]);
           if (kb == sg.kb1 - 1) umma_commit(&acc_full[acc]);
         }
         __syncwarp();
-        if (++bs == C::B_STAGES) { bs = 0; bph ^= 1; }
-        if (++as == C::A_SLOTS) { as = 0; aph ^= 1; }
+        if (++st == C::B_STAGES) { st = 0; ph ^= 1; }
       }
       if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1; }
     }
@@ -316,7 +318,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         if (p.dbg & 2) {
           __syncwarp();
           if (lane == 0) { mbar_arrive(&w_empty[ws]); }
-          mbar_wait(&a_empty[as], aph ^ 1);
+          mbar_wait(&ba_empty[as], aph ^ 1);
           if (lane == 0) { mbar_arrive(&a_full[as]); }
           if (++ws == C::W_STAGES) { ws = 0; wph ^= 1; }
           if (++as == C::A_SLOTS) { as = 0; aph ^= 1; }
@@ -342,7 +344,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[pending]);
         }
-        mbar_wait(&a_empty[as], aph ^ 1);
+        mbar_wait(&ba_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE + as * A_COLS_PER_STAGE;
         const uint32_t t_hi = t_lo + (16u << 16);
