@@ -179,7 +179,7 @@ OB_DEVICE uint32_t vadd4(uint32_t a, uint32_t b) {
 }
 
 template <int BN, bool PER_GROUP>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(104)
 w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_constant__ CUtensorMap w_map,
                  const GemmParams p) {
   using C = Cfg<BN>;
@@ -205,14 +205,16 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
   const int lane = threadIdx.x & 31;
   pdl_trigger();
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&act_map);
-    tma_prefetch_desc(&w_map);
-    for (int i = 0; i < C::W_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 4); }
-    for (int i = 0; i < C::B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&a_full[i], 4); mbar_init(&ba_empty[i], 1); }
-    for (int i = 0; i < C::ACC_BUFS; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&act_map);
+      tma_prefetch_desc(&w_map);
+    }
+    // one barrier per lane: arrival counts are 4 for the barriers the four unpack / epilogue warps arrive on
+    for (int i = lane; i < C::NUM_BARS; i += 32) {
+      uint64_t* b = bars + i;
+      const bool four = (b >= w_empty && b < b_full) || (b >= a_full && b < ba_empty) || (b >= acc_empty);
+      mbar_init(b, four ? 4 : 1);
     }
     mbar_fence_init();
   }
@@ -715,7 +717,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   int grid;
   unsigned cluster = 1;
   // Scheduling choice (cost model in K-block times, constants from tools/gemm_micro.py: the L2 bulk-reduce finalisation
-  // of stream-K costs ~12 K-block times):
+  // of stream-K costs ~18 K-block times (0.27 us each)):
   //   few tiles      -> cluster split-K: k CTAs per tile (k <= 8, tiles*k <= #SMs), reduce-scatter over DSMEM
   //   medium         -> whichever of data-parallel tiles / stream-K is cheaper
   //   many tiles     -> data-parallel tiles
@@ -730,7 +732,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     if (tiles >= 8LL * sms) mode = 0;
     else {
       const long long cost_dp = ((tiles + sms - 1) / sms) * KB;
-      const long long cost_sk = (tiles * KB + sms - 1) / sms + 12;
+      const long long cost_sk = (tiles * KB + sms - 1) / sms + 18;
       mode = cost_sk < cost_dp ? 1 : 0;
     }
   }

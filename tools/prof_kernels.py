@@ -89,6 +89,42 @@ if "attention" in what or "small" in what:
         by = B * ctx * 8 * 136
         print(f"[attention] bs={B} ctx={ctx}: {ms * 1e3:8.1f} us  {by / ms / 1e6:7.1f} GB/s", flush=True)
     if "small" in what:
+        # prefill-sized rows (T = 8192): these ops are pure HBM streams there
+        T = 8192
+        x = torch.randn((T, 4096), dtype=torch.float16, device=dev)
+        d = torch.randn((T, 4096), dtype=torch.float16, device=dev)
+        ho = torch.empty_like(x)
+        g = torch.ones(4096, dtype=torch.float16, device=dev)
+        q = torch.empty((T, 4096), dtype=torch.int8, device=dev)
+        sc = torch.empty(T, dtype=torch.float16, device=dev)
+        sm = torch.empty(T, dtype=torch.float16, device=dev)
+        gu = torch.randn((T, 28672), dtype=torch.float16, device=dev)
+        qm = torch.empty((T, 14336), dtype=torch.int8, device=dev)
+        qkvp = torch.randn((T, 6144), dtype=torch.float16, device=dev)
+        rows = [("add_rms_norm_general", lambda: ops.layernorm_ops.add_rms_norm_general(q, x, d, ho, g, sm, sc, 1e-5), T * 4096 * 7),
+                ("rms_norm_general_fuse_sum", lambda: ops.layernorm_ops.rms_norm_general_fuse_sum(q, x, g, sm, sc, 1e-5, True), T * 4096 * 3),
+                ("invoke_quant_fuse_sum", lambda: ops.fused_kernels.invoke_quant_fuse_sum(q, x, sm, sc), T * 4096 * 3),
+                ("silu_and_mul_quant", lambda: ops.activation_ops.silu_and_mul_quant(qm, gu, sm, sc), T * 14336 * 5)]
+        for name, fn, by in rows:
+            fn()
+            t = timeit(fn, 10)
+            print(f"[small T={T}] {name:28s} {t * 1e3:8.1f} us  {by / t / 1e6:7.1f} GB/s", flush=True)
+        sl = torch.full((8,), 1024, dtype=torch.int32, device=dev)
+        cu = torch.arange(0, 8193, 1024, dtype=torch.int32, device=dev)
+        pad = ops.fused_attention_fine_grained_dense.compute_padding_offsets(cu, 1024, T)
+        m8 = LlamaW4A8(cfg, dev)
+        m8.alloc(8, 1536, 64)
+        fl, rk = torch.ones(8, dtype=torch.int32, device=dev), torch.arange(8, dtype=torch.int32, device=dev)
+
+        def kvw():
+            ops.fused_attention_fine_grained_dense.apply_bias_rope_update_kv_cache(
+                qkvp, sl, None, pad, m8.kv.tables[0], None, fl, rk, 32, 8, 1024, 64, 512, 0, 0, 0, 0, 0, 8, 0, 128, 5e5, 1.0,
+                8192, True, True, True)
+        kvw()
+        t = timeit(kvw, 10)
+        by = T * 6144 * 2 + T * 5120 * 2 + T * 2 * 8 * 68
+        print(f"[small T={T}] {'apply_bias_rope_update_kv_cache':28s} {t * 1e3:8.1f} us  {by / t / 1e6:7.1f} GB/s", flush=True)
+        del x, d, ho, q, gu, qm, qkvp
         x = torch.randn((B, 4096), dtype=torch.float16, device=dev)
         g = torch.ones(4096, dtype=torch.float16, device=dev)
         q = torch.empty((B, 4096), dtype=torch.int8, device=dev)
