@@ -59,7 +59,7 @@ struct Cfg {
   static constexpr int SMEM_STAGING = SMEM_S2 + W_STAGES * S2_STAGE;
   static constexpr int SMEM_TOK = SMEM_STAGING + STAGING;      // float sa[BN], ss[BN]
   static constexpr int SMEM_BAR = SMEM_TOK + BN * 8;
-  static constexpr int NUM_BARS = 2 * W_STAGES + 3 * B_STAGES + 2 * ACC_BUFS;
+  static constexpr int NUM_BARS = 2 * W_STAGES + 4 * B_STAGES + 2 * ACC_BUFS;
   static constexpr int SMEM_MISC = SMEM_BAR + NUM_BARS * 8;    // tmem slot, flags
   static constexpr int SMEM_TOTAL = SMEM_MISC + 64 + 1024;      // + alignment slack
   static_assert(TMEM_A_BASE + A_SLOTS * A_COLS_PER_STAGE <= 512, "TMEM budget");
@@ -81,6 +81,7 @@ struct GemmParams {
   int n_tiles, m_tiles, kb_per_tile;
   int mode;                 // 0 = DP tiles, 1 = stream-K (L2 bulk-reduce), 2 = cluster split-K (DSMEM reduce-scatter)
   int cluster_k;            // mode 2: CTAs per tile
+  int mc;                   // mode 0: activation multicast across a cluster of mc N-tiles (1 = off)
   int units_per_cta;        // SK: K-blocks per CTA
   int group_m;              // DP raster: m-tiles per L2 group
   int w_rows2k;             // weight tensor map variant: 4 rows of 2 KB per K-block instead of 16 rows of 512 B
@@ -105,8 +106,10 @@ struct SegIter {
       end = (int)(((long long)KB * (r + 1)) / k);
       step = 0;
     } else if (mode == 0) {
-      tile = blockIdx.x;
-      step = gridDim.x;
+      // with multicast the unit of scheduling is a super-tile (mc N-tiles x one token tile) per cluster
+      tile = blockIdx.x / p.mc;
+      step = gridDim.x / p.mc;
+      total_tiles = (p.n_tiles / p.mc) * p.m_tiles;
     } else {
       long long tot = (long long)total_tiles * KB;
       long long b = (long long)blockIdx.x * p.units_per_cta;
@@ -160,12 +163,14 @@ struct KbIter {
 
 OB_DEVICE void tile_coords(const GemmParams& p, int tile, int& nt, int& mt) {
   if (p.mode == 0) {
-    int per_group = p.group_m * p.n_tiles;
+    const int n_super = p.n_tiles / p.mc;
+    int per_group = p.group_m * n_super;
     int g = tile / per_group;
     int r = tile - g * per_group;
     int gm = min(p.group_m, p.m_tiles - g * p.group_m);
     nt = r / gm;
     mt = g * p.group_m + (r - nt * gm);
+    if (p.mc > 1) nt = nt * p.mc + (int)cluster_ctarank();
   } else {
     nt = tile / p.m_tiles;
     mt = tile - nt * p.m_tiles;
@@ -179,9 +184,9 @@ OB_DEVICE uint32_t vadd4(uint32_t a, uint32_t b) {
 }
 
 template <int BN, bool PER_GROUP>
-__global__ void __maxnreg__(104)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_constant__ CUtensorMap w_map,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap act_mc_map, const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -196,7 +201,8 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
   uint64_t* b_full = w_empty + C::W_STAGES;               // activation tile landed
   uint64_t* a_full = b_full + C::B_STAGES;                // unpack warps filled the TMEM A slot
   uint64_t* ba_empty = a_full + C::B_STAGES;              // MMAs that read activation stage s / TMEM slot s retired
-  uint64_t* acc_full = ba_empty + C::B_STAGES;
+  uint64_t* b_empty_mc = ba_empty + C::B_STAGES;          // multicast only: every CTA of the cluster released stage s
+  uint64_t* acc_full = b_empty_mc + C::B_STAGES;
   uint64_t* acc_empty = acc_full + C::ACC_BUFS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::SMEM_MISC);
   int* sFlag = reinterpret_cast<int*>(smem + C::SMEM_MISC + 8);
@@ -214,7 +220,8 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     for (int i = lane; i < C::NUM_BARS; i += 32) {
       uint64_t* b = bars + i;
       const bool four = (b >= w_empty && b < b_full) || (b >= a_full && b < ba_empty) || (b >= acc_empty);
-      mbar_init(b, four ? 4 : 1);
+      const bool mcb = (b >= b_empty_mc && b < acc_full);
+      mbar_init(b, mcb ? (uint32_t)p.mc : (four ? 4u : 1u));
     }
     mbar_fence_init();
   }
@@ -222,7 +229,8 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (p.mode == 2 && !(p.dbg & 16)) cluster_barrier();  // all CTAs of the cluster run before any DSMEM store targets them
+  // all CTAs of the cluster run (barriers initialised) before any DSMEM store / multicast copy / remote arrive targets them
+  if ((p.mode == 2 && !(p.dbg & 16)) || p.mc > 1) cluster_barrier();
   const uint32_t tmem_base = *tmem_slot;
 
 
@@ -258,11 +266,27 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       KbIter it;
       it.init(p);
       int stage = 0, phase = 0;
-      while (it.next(p)) {
-        mbar_wait(&ba_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&b_full[stage], (p.dbg & 32) ? 0 : C::B_STAGE);
-        if (!(p.dbg & 32)) tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, it.mt * BN, &b_full[stage]);
-        if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
+      if (p.mc > 1) {
+        // Multicast: this CTA fetches rows [rank*BN/mc, (rank+1)*BN/mc) of the token tile and delivers them to every
+        // CTA of the cluster (they work on different weight rows, same tokens, same K-block): L2 is read once per
+        // cluster instead of once per CTA.  A stage may be refilled only when all mc CTAs have retired its MMAs.
+        const int rank = (int)cluster_ctarank();
+        const int rows = BN / p.mc;
+        const uint16_t mask = (uint16_t)((1u << p.mc) - 1u);
+        while (it.next(p)) {
+          mbar_wait(&b_empty_mc[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&b_full[stage], C::B_STAGE);
+          tma_load_2d_mc(sB + stage * C::B_STAGE + rank * rows * BK, &act_mc_map, it.kb * BK, it.mt * BN + rank * rows,
+                         &b_full[stage], mask);
+          if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
+        }
+      } else {
+        while (it.next(p)) {
+          mbar_wait(&ba_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&b_full[stage], (p.dbg & 32) ? 0 : C::B_STAGE);
+          if (!(p.dbg & 32)) tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, it.mt * BN, &b_full[stage]);
+          if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -295,6 +319,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
             umma_i8_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1u);
           }
           umma_commit(&ba_empty[st]);
+          if (p.mc > 1) umma_commit_mc(&b_empty_mc[st], (uint16_t)((1u << p.mc) - 1u));
           if (kb == sg.kb1 - 1) umma_commit(&acc_full[acc]);
         }
         __syncwarp();
@@ -581,6 +606,8 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     if (p.mode == 2 && !cluster_done) cluster_barrier();
   }
   if (p.mode == 2 && warp < 8) cluster_barrier();  // non-epilogue warps: every thread of the cluster arrives once
+  __syncwarp();
+  if (p.mc > 1) cluster_barrier();  // peers may still multicast-arrive on this CTA's barriers until they are done too
 
   tc_fence_before();
   __syncthreads();
@@ -677,8 +704,8 @@ static int ensure_workspace(int dev, int sms) {
 }
 
 template <int BN, bool PG>
-static int launch(const CUtensorMap& map, const CUtensorMap& wmap, GemmParams& p, int grid, unsigned cluster,
-                  cudaStream_t st) {
+static int launch(const CUtensorMap& map, const CUtensorMap& wmap, const CUtensorMap& mcmap, GemmParams& p, int grid,
+                  unsigned cluster, cudaStream_t st) {
   using C = Cfg<BN>;
   auto kern = w4a8_gemm_kernel<BN, PG>;
   static bool attr_done = false;
@@ -687,7 +714,26 @@ static int launch(const CUtensorMap& map, const CUtensorMap& wmap, GemmParams& p
       return OB_ERR_CUDA;
     attr_done = true;
   }
-  return launch_pdl_cluster(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, cluster, map, wmap, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
+  if (p.mc > 1) {
+    // persistent multicast clusters: as many as can be co-resident (GPC sizes limit how many clusters of mc fit)
+    static int max_clusters[9] = {0};
+    if (!max_clusters[p.mc]) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(p.mc * 64);
+      cfg.blockDim = dim3(NUM_THREADS);
+      cfg.dynamicSmemBytes = C::SMEM_TOTAL;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = p.mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = 1;
+      max_clusters[p.mc] = n;
+    }
+    const int super_tiles = (p.n_tiles / p.mc) * p.m_tiles;
+    grid = std::min(super_tiles, max_clusters[p.mc]) * p.mc;
+  }
+  return launch_pdl_cluster(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, cluster, map, wmap, mcmap, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
 int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
@@ -753,15 +799,27 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     p.group_m = std::max(1, 8192 / BN);  // 8192 tokens' activations stay L2-resident while all n-tiles sweep
     p.units_per_cta = p.kb_per_tile;
     grid = (int)std::min<long long>(tiles, sms);
+    // Feed-bound regime (many tiles per SM): share the activation tile across a cluster of mc N-tiles by TMA
+    // multicast.  OB_GEMM_MC = 1 / 2 / 4 overrides (experiments).
+    int mc = (tiles >= 4LL * sms && BN >= 64) ? ((p.n_tiles % 4 == 0) ? 4 : (p.n_tiles % 2 == 0 ? 2 : 1)) : 1;
+    { const char* e3 = getenv("OB_GEMM_MC"); if (e3) mc = atoi(e3); }
+    if (mc < 1 || mc > 4 || (mc & (mc - 1)) || p.n_tiles % mc || BN % (8 * mc) || a.force_ctas > 0) mc = 1;
+    p.mc = mc;
+    if (mc > 1) cluster = (unsigned)mc;
   }
+  if (p.mc < 1) p.mc = 1;
   CUtensorMap map;
   if (int e = make_act_map(&map, a.in_feats, a.M, a.K, BN)) return e;
+  CUtensorMap mcmap = map;
+  if (p.mc > 1) {
+    if (int e = make_act_map(&mcmap, a.in_feats, a.M, a.K, BN / p.mc)) return e;
+  }
   CUtensorMap wmap;
   { const char* e2 = getenv("OB_GEMM_W2K"); p.w_rows2k = (e2 && atoi(e2)) ? 1 : 0; }
   if (int e = make_w_map(&wmap, a.qweight, a.N, a.K, p.w_rows2k != 0)) return e;
 #define OB_LAUNCH(bn)                                                              \
   case bn:                                                                         \
-    return per_group ? launch<bn, true>(map, wmap, p, grid, cluster, st) : launch<bn, false>(map, wmap, p, grid, cluster, st);
+    return per_group ? launch<bn, true>(map, wmap, mcmap, p, grid, cluster, st) : launch<bn, false>(map, wmap, mcmap, p, grid, cluster, st);
   switch (BN) {
     OB_LAUNCH(16)
     OB_LAUNCH(32)

@@ -124,3 +124,29 @@ def test_linearity_property_full_size():
                                z.cpu().numpy(), ss[rows].cpu().numpy())
     got = o1[rows].cpu().numpy().astype(np.float32)
     assert np.abs(got - ref.astype(np.float32)).max() <= REL_TOL * np.abs(ref.astype(np.float32)).max()
+
+
+@pytest.mark.parametrize("per_group", [False, True])
+@pytest.mark.parametrize("mc,M,N,K", [(2, 300, 1024, 1024), (4, 300, 1024, 2048), (4, 128, 512, 512), (2, 1000, 768, 1024)])
+def test_activation_multicast_clusters(mc, M, N, K, per_group, monkeypatch):
+    """Prefill path: the activation tile is TMA-multicast to a cluster of mc CTAs that own different weight rows
+    (same tokens, same K-block); results must not depend on the cluster size, including the token tail."""
+    monkeypatch.setenv("OB_GEMM_MC", str(mc))
+    assert run(M, N, K, per_group, seed=mc * 1000 + M, bn=128 if M > 64 else 0, mode=0) > 0.999
+
+
+def test_prefill_shape_multicast_matches_unicast(monkeypatch):
+    """M = 4096 tokens x a Llama-3-8B sized layer slice: multicast (auto) and unicast outputs are bit-identical
+    (INT32 accumulation is exact, the epilogue is per element)."""
+    from omniserve_b200 import _lib as L
+    d = make_gemm_inputs(4096, 6144, 1024, 5)
+    outs = []
+    for mc in ("1", "4", "2"):
+        monkeypatch.setenv("OB_GEMM_MC", mc)
+        out = torch.empty((4096, 6144), dtype=torch.float16, device="cuda")
+        ta, tq, ts1, tsa, tsz, tss = (t(d[k]) for k in ("a", "qw", "s1", "sa", "szs", "ssum"))
+        assert L.lib().ob_w4a8_gemm_per_chn(L.ptr(ta), L.ptr(tq), L.ptr(ts1), L.ptr(tsa), L.ptr(tsz), L.ptr(tss), L.ptr(out),
+                                            4096, 6144, 1024, 6144, L.stream()) == 0
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

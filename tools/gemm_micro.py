@@ -47,6 +47,18 @@ def run(M, N, K, mode=-1, bn=0, ctas=0, tag=""):
           f"{by / us / 1e3:8.1f} GB/s  {2.0 * M * N * K / us / 1e6:8.1f} TOPS", flush=True)
 
 
+if __name__ == "__main__" and os.environ.get("OB_MC_EXP"):
+    for mc in ("1", "2", "4"):
+        os.environ["OB_GEMM_MC"] = mc
+        run(8192, 6144, 4096, tag=f"prefill qkv mc={mc}")
+        run(8192, 28672, 4096, tag=f"prefill gate_up mc={mc}")
+        run(8192, 4096, 14336, tag=f"prefill down mc={mc}")
+        run(8192, 4096, 4096, tag=f"prefill o mc={mc}")
+    del os.environ["OB_GEMM_MC"]
+    run(2048, 28672, 4096, tag="M=2048 gate_up auto")
+    run(512, 28672, 4096, tag="M=512 gate_up auto")
+    sys.exit(0)
+
 if __name__ == "__main__" and os.environ.get("OB_STREAM_EXP"):
     # what bounds the per-K-block time of the load pipeline?  (results invalid for dbg != 0: timing only)
     for w2k in ("0", "1"):
