@@ -621,65 +621,82 @@ OB_DEVICE void quant_store_pairs(const float (&x)[4], uint8_t* row, __half* scal
 }
 
 __global__ void __launch_bounds__(256) kv4_prefill_write_kernel(const PrefillParams p) {
+  // cos / sin depend on (position, pair index) only: they are evaluated once per token (64 accurate sincosf) and
+  // shared by the token's 40 q / k heads through shared memory; powf(base, 2d/rot) once per CTA.
+  constexpr int TOK = 4;                       // tokens per CTA iteration (256 threads = 4 x 64 pair indices)
+  __shared__ float pw[DH / 2];
+  __shared__ float cs_s[TOK][DH / 2], sn_s[TOK][DH / 2];
+  __shared__ int b_s[TOK], pos_s[TOK], len_s[TOK];
   pdl_trigger();
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int warps_per_cta = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int heads_total = p.Hq + 2 * p.Hkv;
-  const long long items = (long long)p.T * heads_total;
   const int row_elems = heads_total * DH;
   const int half_rot = p.rotary_dim >> 1;
-  for (long long it = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); it < items;
-       it += (long long)gridDim.x * warps_per_cta) {
-    const int t = (int)(it / heads_total);
-    const int hh = (int)(it - (long long)t * heads_total);
-    const int g = t + p.padding_offset[t];
-    const int b = g / p.max_seq_len;
-    const int pos = g - b * p.max_seq_len;
-    __half* src = p.qkv + (size_t)t * row_elems + (size_t)hh * DH;
-    const __half2 lo = *reinterpret_cast<const __half2*>(src + 2 * lane);
-    const __half2 hi = *reinterpret_cast<const __half2*>(src + 64 + 2 * lane);
-    float x[4] = {__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi)};
-    const bool is_v = hh >= p.Hq + p.Hkv;
-    if (!is_v) {
-      // pairs (2l, 2l+64) and (2l+1, 2l+65); rotary_dim == 128 on this path (Dh == rotary_dim)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int d = 2 * lane + e;
-        if (d < half_rot) {
-          const float inv_freq = ((float)pos * p.rope_scale) / powf(p.rope_base, (float)(2 * d) / (float)p.rotary_dim);
-          float sn, cs;
-          sincosf(inv_freq, &sn, &cs);
-          const float a = x[e], bb = x[2 + e];
-          x[e] = __half2float(__float2half_rn(cs * a - sn * bb));
-          x[2 + e] = __half2float(__float2half_rn(cs * bb + sn * a));
-        }
+  if (tid < DH / 2) pw[tid] = powf(p.rope_base, (float)(2 * tid) / (float)p.rotary_dim);
+  pdl_wait();
+  __syncthreads();
+  for (int t0 = blockIdx.x * TOK; t0 < p.T; t0 += gridDim.x * TOK) {
+    {
+      const int j = tid >> 6, d = tid & 63, t = t0 + j;
+      if (t < p.T) {
+        const int g = t + p.padding_offset[t];
+        const int b = g / p.max_seq_len;
+        const int pos = g - b * p.max_seq_len;
+        if (d == 0) { b_s[j] = b; pos_s[j] = pos; len_s[j] = p.seq_lens[b]; }
+        if (d < half_rot) sincosf(((float)pos * p.rope_scale) / pw[d], &sn_s[j][d], &cs_s[j][d]);
       }
-      *reinterpret_cast<__half2*>(src + 2 * lane) = __floats2half2_rn(x[0], x[1]);
-      *reinterpret_cast<__half2*>(src + 64 + 2 * lane) = __floats2half2_rn(x[2], x[3]);
     }
-    if (hh < p.Hq) continue;
-    const int hkv = is_v ? hh - p.Hq - p.Hkv : hh - p.Hq;
-    const bool retr = p.retrieval_flags ? p.retrieval_flags[hkv] != 0 : true;
-    const int rank = p.head_rank ? p.head_rank[hkv] : hkv;
-    const int L = p.seq_lens[b];
-    int tabidx = pos >> 6;
-    const int64_t* tab;
-    int hpool;
-    if (retr) {
-      tab = p.r_tab + (size_t)b * 2 * p.r_max_pages + (is_v ? p.r_max_pages : 0);
-      hpool = p.r_hpool;
-    } else {
-      if (!(pos < p.sink_tok || pos >= L - p.local_tok)) continue;  // applyBiasRopeUpdateKVCache.h:303-311
-      tab = p.s_tab + (size_t)b * 2 * p.s_max_pages + (is_v ? p.s_max_pages : 0);
-      hpool = p.s_hpool;
-      tabidx = tabidx < p.sink_blk ? tabidx : p.sink_blk + (tabidx - p.sink_blk) % p.local_blk;
+    __syncthreads();
+    const int items = min(TOK, p.T - t0) * heads_total;
+    for (int it = warp; it < items; it += 8) {
+      const int j = it / heads_total;
+      const int hh = it - j * heads_total;
+      const int t = t0 + j;
+      const int b = b_s[j], pos = pos_s[j];
+      __half* src = p.qkv + (size_t)t * row_elems + (size_t)hh * DH;
+      const __half2 lo = *reinterpret_cast<const __half2*>(src + 2 * lane);
+      const __half2 hi = *reinterpret_cast<const __half2*>(src + 64 + 2 * lane);
+      float x[4] = {__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi)};
+      const bool is_v = hh >= p.Hq + p.Hkv;
+      if (!is_v) {
+        // pairs (2l, 2l+64) and (2l+1, 2l+65); rotary_dim == 128 on this path (Dh == rotary_dim)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int d = 2 * lane + e;
+          if (d < half_rot) {
+            const float sn = sn_s[j][d], cs = cs_s[j][d];
+            const float a = x[e], bb = x[2 + e];
+            x[e] = __half2float(__float2half_rn(cs * a - sn * bb));
+            x[2 + e] = __half2float(__float2half_rn(cs * bb + sn * a));
+          }
+        }
+        *reinterpret_cast<__half2*>(src + 2 * lane) = __floats2half2_rn(x[0], x[1]);
+        *reinterpret_cast<__half2*>(src + 64 + 2 * lane) = __floats2half2_rn(x[2], x[3]);
+      }
+      if (hh < p.Hq) continue;
+      const int hkv = is_v ? hh - p.Hq - p.Hkv : hh - p.Hq;
+      const bool retr = p.retrieval_flags ? p.retrieval_flags[hkv] != 0 : true;
+      const int rank = p.head_rank ? p.head_rank[hkv] : hkv;
+      const int L = len_s[j];
+      int tabidx = pos >> 6;
+      const int64_t* tab;
+      int hpool;
+      if (retr) {
+        tab = p.r_tab + (size_t)b * 2 * p.r_max_pages + (is_v ? p.r_max_pages : 0);
+        hpool = p.r_hpool;
+      } else {
+        if (!(pos < p.sink_tok || pos >= L - p.local_tok)) continue;  // applyBiasRopeUpdateKVCache.h:303-311
+        tab = p.s_tab + (size_t)b * 2 * p.s_max_pages + (is_v ? p.s_max_pages : 0);
+        hpool = p.s_hpool;
+        tabidx = tabidx < p.sink_blk ? tabidx : p.sink_blk + (tabidx - p.sink_blk) % p.local_blk;
+      }
+      uint8_t* page = reinterpret_cast<uint8_t*>(tab[tabidx]);
+      const int slot = pos & 63;
+      const int data_bytes = hpool * TPB * (DH / 2);
+      __half* sc = reinterpret_cast<__half*>(page + data_bytes) + rank * TPB + slot;
+      quant_store_pairs(x, page + (size_t)rank * TPB * (DH / 2) + slot * (DH / 2), sc, sc + hpool * TPB, lane);
     }
-    uint8_t* page = reinterpret_cast<uint8_t*>(tab[tabidx]);
-    const int slot = pos & 63;
-    const int data_bytes = hpool * TPB * (DH / 2);
-    __half* sc = reinterpret_cast<__half*>(page + data_bytes) + rank * TPB + slot;
-    quant_store_pairs(x, page + (size_t)rank * TPB * (DH / 2) + slot * (DH / 2), sc, sc + hpool * TPB, lane);
+    __syncthreads();
   }
 }
 
@@ -775,8 +792,7 @@ int kv4_prefill_write_run(const KV4PrefillArgs& a, cudaStream_t st) {
   p.sink_tok = a.sink_tokens; p.local_tok = a.local_tokens; p.sink_blk = a.sink_blocks;
   p.local_blk = a.local_blocks > 0 ? a.local_blocks : 1;
   p.rotary_dim = a.rotary_dim; p.rope_base = a.rotary_base; p.rope_scale = a.rotary_scale;
-  const long long items = (long long)a.T * (a.Hq + 2 * a.Hkv);
-  const int blocks = (int)std::min<long long>((items + 7) / 8, 148LL * 16);
+  const int blocks = (int)std::min<long long>(((long long)a.T + 3) / 4, 148LL * 8);
   return launch_pdl(kv4_prefill_write_kernel, dim3(blocks), dim3(256), 0, st, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 

@@ -799,9 +799,12 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     p.group_m = std::max(1, 8192 / BN);  // 8192 tokens' activations stay L2-resident while all n-tiles sweep
     p.units_per_cta = p.kb_per_tile;
     grid = (int)std::min<long long>(tiles, sms);
-    // Feed-bound regime (many tiles per SM): share the activation tile across a cluster of mc N-tiles by TMA
-    // multicast.  OB_GEMM_MC = 1 / 2 / 4 overrides (experiments).
-    int mc = (tiles >= 4LL * sms && BN >= 64) ? ((p.n_tiles % 4 == 0) ? 4 : (p.n_tiles % 2 == 0 ? 2 : 1)) : 1;
+    // Activation multicast across a cluster of mc N-tiles (TMA .multicast::cluster) is implemented and tested, but
+    // measured SLOWER than unicast on B200 for the Llama prefill shapes (M = 8192: qkv 235 vs 201 us at mc = 2, 250 at
+    // mc = 4; profiles/r1_summary.md): L2 read traffic is not the limiter (the shared-memory port is: TMA writes +
+    // packed-weight reads + UMMA B-operand reads ~ 48 KB per K-block), and lock-stepping the cluster costs more than
+    // the saved L2 reads.  Opt-in for experiments: OB_GEMM_MC = 2 / 4.
+    int mc = 1;
     { const char* e3 = getenv("OB_GEMM_MC"); if (e3) mc = atoi(e3); }
     if (mc < 1 || mc > 4 || (mc & (mc - 1)) || p.n_tiles % mc || BN % (8 * mc) || a.force_ctas > 0) mc = 1;
     p.mc = mc;
