@@ -230,6 +230,67 @@ def prefill_gemm_tops(model, M=8192):
     return out
 
 
+INT8_PEAK_RECORDED = 4350.0  # TOPS, tools/umma_rate.cu on this pool's B200 (profiles/r1_umma_rate.log): 8188 MAC/clk/SM
+
+
+def int8_peak():
+    """Dense INT8 tensor-pipe peak measured on this GPU with the stand-alone tcgen05.mma probe (128x128x32 kind::i8
+    MMAs issued back to back on all SMs, no loads); falls back to the value recorded in profiles/ when the probe
+    binary was not built."""
+    exe = os.path.join(ROOT, "tools", "_build", "umma_rate")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+        for ln in out.splitlines():
+            if ln.startswith("i8  128x128x32  A=tmem") and "ctas=148" in ln:
+                return float(ln.split("->")[1].split()[0]) * 1000.0, "measured live (tools/umma_rate.cu)"
+    except Exception:
+        pass
+    return INT8_PEAK_RECORDED, "recorded (profiles/r1_umma_rate.log)"
+
+
+def measure_tp(cfg, dev, rank, world, steps, warmup):
+    """Tensor-parallel decode (column/row sharded W4A8 layers, one NCCL all-reduce after o_proj and after down_proj,
+    captured in the CUDA graph): same global batch of 64 over all GPUs (strong scaling)."""
+    import torch.distributed as dist
+    from omniserve_b200.model import DecodeGraph, LlamaW4A8
+    model = LlamaW4A8(cfg, dev, rank, world)
+    max_ctx = PROMPT_LEN + GEN_LEN
+    model.alloc(BATCH, max_ctx, PREFILL_SUB_BATCH * PROMPT_LEN)
+    g = torch.Generator().manual_seed(42)
+    prompts = torch.randint(0, cfg.vocab_size, (BATCH, PROMPT_LEN), generator=g)
+    first, chunk_ms = [], []
+    for s0 in range(0, BATCH, PREFILL_SUB_BATCH):
+        toks = prompts[s0:s0 + PREFILL_SUB_BATCH].reshape(-1).to(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        first.append(model.prefill(toks, [PROMPT_LEN] * PREFILL_SUB_BATCH, seq_offset=s0))
+        c1.record()
+        chunk_ms.append((c0, c1))
+    torch.cuda.synchronize()
+    per_chunk = sorted(x.elapsed_time(y) for x, y in chunk_ms)
+    prefill_ms = sum(per_chunk[:-1]) * len(per_chunk) / max(1, len(per_chunk) - 1)
+    graph = DecodeGraph(model, max_ctx)
+    graph.tokens.copy_(torch.cat(first))
+    for _ in range(max(3, warmup)):
+        graph.graph.replay()
+    dist.barrier(); torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        graph.graph.replay()
+    t1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    tms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    del graph, model
+    torch.cuda.empty_cache()
+    return {"value": BATCH * steps / (ms / 1e3), "unit": "tok/s", "ms_per_step": ms / steps, "steps": steps,
+            "parallelism": f"tp{world}", "scaling": "strong", "global_batch": BATCH,
+            "prefill_tok_per_s": BATCH * PROMPT_LEN / (prefill_ms / 1e3),
+            "collective": "NCCL all-reduce (fp16 sum, [64, 4096]) after o_proj and after down_proj, inside the CUDA graph"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -238,7 +299,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (result is then marked invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "dp", "tp"],
+                    help="N > 1: dp = one bs=64 replica per GPU (weak scaling, no data-path collective; what an 8B "
+                         "model is served with), tp = tensor parallel over all GPUs (strong scaling, NCCL all-reduce "
+                         "after o_proj and down_proj).  auto = dp, with the tp measurement added under \"tp\".")
     a = ap.parse_args()
+    # Keep stdout clean for the ONE JSON line: libraries (NCCL banner, warnings) print to fd 1 in worker processes.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,7 +320,9 @@ def main():
     if use_dist:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    tp = world if use_dist else 1
+    mode = "dp" if a.parallelism in ("auto", "dp") else "tp"
+    tp = world if (use_dist and mode == "tp") else 1
+    replicas = world if (use_dist and mode == "dp") else 1
 
     from omniserve_b200.model import DecodeGraph, LlamaConfig, LlamaW4A8, Ops, kernel_launches_per_decode_step
     cfg = LlamaConfig.llama3_8b()
@@ -263,11 +334,12 @@ def main():
         try:
             ops = Ops(ref_loader())
         except Exception as e:  # oracle/_ref not shipped
-            print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"}))
+            real_stdout.write(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"}) + "\n")
+            real_stdout.flush()
             return 0
         model = LlamaW4A8(cfg, dev, 0, 1, fuse_silu_quant=False, ops=ops)
     else:
-        model = LlamaW4A8(cfg, dev, rank if use_dist else 0, tp)
+        model = LlamaW4A8(cfg, dev, rank if tp > 1 else 0, tp, seed=rank if replicas > 1 else 0)
     max_ctx = PROMPT_LEN + GEN_LEN
     model.alloc(BATCH, max_ctx, PREFILL_SUB_BATCH * PROMPT_LEN)
 
@@ -378,8 +450,8 @@ def main():
     run_steps(3, e2e=True)
     ms_e2e = timed(a.steps, e2e=True)
 
-    value = BATCH * a.steps / (ms / 1e3)
-    e2e_value = BATCH * a.steps / (ms_e2e / 1e3)
+    value = BATCH * replicas * a.steps / (ms / 1e3)
+    e2e_value = BATCH * replicas * a.steps / (ms_e2e / 1e3)
 
     # ---------------------------------------------------------------- per-kernel roofline (rank 0 shapes)
     mid_ctx = PROMPT_LEN + GEN_LEN // 2
@@ -401,30 +473,42 @@ def main():
     prefill = None
     if a.impl == "ours" and tp == 1 and not skip_prefill:
         pg = prefill_gemm_tops(model)
-        prefill = {"tok_per_s": BATCH * PROMPT_LEN / (prefill_ms_steady / 1e3), "ms": prefill_ms_steady,
+        i8_peak, i8_src = int8_peak() if rank == 0 else (INT8_PEAK_RECORDED, "")
+        prefill = {"tok_per_s": BATCH * replicas * PROMPT_LEN / (prefill_ms_steady / 1e3), "ms": prefill_ms_steady,
                    "ms_incl_first_chunk_init": prefill_ms, "gemm_M8192": pg,
-                   "int8_peak_tops_provisional": 2 * bf16_peak,
-                   "gemm_frac_of_provisional_int8_peak": pg["all"]["tops"] / (2 * bf16_peak)}
+                   "int8_peak_tops": i8_peak, "int8_peak_source": i8_src,
+                   "gemm_frac_of_int8_peak": pg["all"]["tops"] / i8_peak}
+
+    step_floor_ms = (model.weight_bytes() + model.lm_head.numel() * 2
+                     + BATCH * mid_ctx * model.hkv * 136 * cfg.num_hidden_layers) / hbm_peak / 1e6
+    tp_result = None
+    if use_dist and mode == "dp" and a.parallelism == "auto" and os.environ.get("OB_BENCH_TP", "1") != "0":
+        tp_result = measure_tp(cfg, dev, rank, world, min(a.steps, 64), a.warmup)
 
     if rank != 0:
         return 0
     line = {
         "metric": "decode tok/s Llama-3-8B W4A8KV4 bs=64",
         "value": value, "unit": "tok/s", "n_gpus": world if use_dist else 1, "steps": a.steps, "warmup": max(3, a.warmup),
-        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak" if mode == "dp" else "strong",
+        "vs_baseline": None,
         "dtype": "int8 (W4A8, s32 accumulate) + fp16 KV4 attention", "data": "synthetic (random-init weights, random prompts)",
         "config": {"workload": "Llama-3-8B W4A8KV4 per-channel, qserve_benchmark.py semantics bs=64 in=1024 out=512: "
-                               "decode steps after a real 64x1024 prefill", "global_batch": BATCH, "prompt_len": PROMPT_LEN,
-                   "ctx_at_first_timed_step": ctx_start, "parallelism": f"tp{tp}", "cuda_graph": a.impl == "ours",
+                               "decode steps after a real 64x1024 prefill", "global_batch": BATCH * replicas, "prompt_len": PROMPT_LEN,
+                   "ctx_at_first_timed_step": ctx_start,
+                   "parallelism": (f"dp{replicas} (one bs={BATCH} replica per GPU, no data-path collective)" if replicas > 1
+                                   else f"tp{tp}"), "cuda_graph": a.impl == "ours",
                    "l2": "per-step working set (3.5 GB W4 weights + 2.8 GB KV4 + 1 GB lm_head) >> 126 MB L2; no flush needed",
                    "layers": cfg.num_hidden_layers},
-        "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": BATCH * 8, "d2h_bytes_per_step": BATCH * 8,
+        "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": BATCH * replicas * 8,
+                "d2h_bytes_per_step": BATCH * replicas * 8,
                 "ms_per_step": ms_e2e / a.steps},
-        "gpu_launches": (kernel_launches_per_decode_step(cfg, model.fuse_silu_quant) * a.steps) if a.impl == "ours" else 0,
+        "gpu_launches": (kernel_launches_per_decode_step(cfg, True) * a.steps * replicas) if a.impl == "ours" else 0,
         "clocks": clocks, "roofline": roof, "kernels": kernels, "prefill": prefill,
-        "step_floor_ms_at_measured_hbm": (model.weight_bytes() + model.lm_head.numel() * 2
-                                          + BATCH * mid_ctx * model.hkv * 136 * cfg.num_hidden_layers) / hbm_peak / 1e6,
+        "step_floor_ms_at_measured_hbm": step_floor_ms,
     }
+    if tp_result is not None:
+        line["tp"] = tp_result
     if a.layers:
         line["invalid"] = "debug run with fewer layers"
     if skip_prefill:
@@ -435,7 +519,8 @@ def main():
                                   "rebuilt for sm_100 by oracle/build_ref.py, same decoder-step sequencing, eager launches")
     if not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(LlamaConfig.llama3_8b())
-    print(json.dumps(line))
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()
     return 0
 
 

@@ -104,6 +104,11 @@ typedef struct ob_kv4_decode_args {
    * kmax / kmin statistics of its sub-chunk (element-wise max / min with what is stored there). */
   int tokens_per_sub_chunk;
   int hidden_dim_per_retrieval_token;                 /* num_retrieval_kv_heads * head_dim */
+  /* Extension (not in the reference): fuse the per-token INT8 quantisation that follows the attention in
+   * llama_w4a8_unpad.py:354 (invoke_quant / invoke_quant_fuse_sum of the [B, Hq*128] output) into this call.  NULL =
+   * off.  quant_out int8 [B, Hq*128], quant_scale fp16 [B], quant_sum fp16 [B] or NULL; bit-identical to the two-op
+   * chain. */
+  void* quant_out; void* quant_scale; void* quant_sum;
 } ob_kv4_decode_args;
 int ob_kv4_single_query_attention(const ob_kv4_decode_args* args, void* stream);
 

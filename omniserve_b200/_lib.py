@@ -36,6 +36,7 @@ class KV4DecodeArgs(C.Structure):
         ("rotary_embedding_dim", c_i), ("rotary_base", c_f), ("rotary_scale", c_f),
         ("force_split", c_i),
         ("tokens_per_sub_chunk", c_i), ("hidden_dim_per_retrieval_token", c_i),
+        ("quant_out", c_p), ("quant_scale", c_p), ("quant_sum", c_p),
     ]
 
 

@@ -18,7 +18,8 @@ def _check_qkv(q, k, v):
 
 def single_query(q, k, v, r_tab, s_tab, flags, rank, dyn, lengths, tokens_per_block, n_r_heads, n_s_heads,
                  sink, local, sink_blk, local_blk, timestep, rot_dim, rot_base, rot_scale, force_split=0,
-                 tokens_per_sub_chunk=0, hidden_dim_per_retrieval_token=0):
+                 tokens_per_sub_chunk=0, hidden_dim_per_retrieval_token=0, quant=None):
+    """quant = (out_i8 [B, Hq*Dh], scale fp16 [B], sum fp16 [B] or None): also quantise the output row per token."""
     _check_qkv(q, k, v)
     B, Hq, Dh = q.shape
     Hkv = k.shape[1]
@@ -46,6 +47,12 @@ def single_query(q, k, v, r_tab, s_tab, flags, rank, dyn, lengths, tokens_per_bl
     a.rotary_embedding_dim, a.rotary_base, a.rotary_scale = int(rot_dim), float(rot_base), float(rot_scale)
     a.force_split = force_split
     a.tokens_per_sub_chunk, a.hidden_dim_per_retrieval_token = int(tokens_per_sub_chunk), int(hidden_dim_per_retrieval_token)
+    if quant is not None:
+        qo, qs, qsum = quant
+        L.require_cuda(qo, qs, qsum)
+        if qo.dtype != torch.int8 or not qo.is_contiguous() or qo.numel() != B * Hq * Dh:
+            raise RuntimeError("fused quant output must be a contiguous int8 [B, Hq*Dh] tensor")
+        a.quant_out, a.quant_scale, a.quant_sum = L.ptr(qo), L.ptr(qs), L.ptr(qsum)
     L.check(L.lib().ob_kv4_single_query_attention(C.byref(a), L.stream()), "single_query_attention")
     return out
 

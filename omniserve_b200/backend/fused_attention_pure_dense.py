@@ -21,6 +21,23 @@ def single_query_attention(q, k, v, kv_pointers, length_per_sample_, alibi_slope
                           0, 0, 0, 0, timestep, rotary_embedding_dim, rotary_base, 1.0)
 
 
+def single_query_attention_quant(q, k, v, kv_pointers, length_per_sample_, alibi_slopes_, memory_max_seqlen,
+                                 tokens_per_block, size_per_token, timestep, rotary_embedding_dim, rotary_base,
+                                 neox_rotary_style, int4_kv_cache, kv_cache_with_zeros, quant_out, quant_sum, quant_scale):
+    """Extension (not in the reference): single_query_attention followed by fused_kernels.invoke_quant(_fuse_sum) of
+    its [B, Hq*Dh] output (llama_w4a8_unpad.py:351-354) in ONE launch -- the last CTA of each sequence to finish
+    quantises the row.  quant_sum may be None.  Bit-identical to the two-op chain."""
+    A._require_kv4(int4_kv_cache, kv_cache_with_zeros)
+    if alibi_slopes_ is not None or not neox_rotary_style:
+        raise NotImplementedError("alibi / GPT-J rotary are not used by the Llama path")
+    Hkv, Dh = k.shape[1], k.shape[-1]
+    if size_per_token != Hkv * Dh // 2:
+        raise RuntimeError("size_per_token must be num_kv_heads * head_dim / 2 for KV4")
+    return A.single_query(q, k, v, kv_pointers, None, None, None, None, length_per_sample_, tokens_per_block, Hkv, 0,
+                          0, 0, 0, 0, timestep, rotary_embedding_dim, rotary_base, 1.0,
+                          quant=(quant_out, quant_scale, quant_sum))
+
+
 def apply_bias_rope_update_kv_cache(*args, **kwargs):
     from .fused_attention_fine_grained_dense import apply_bias_rope_update_kv_cache as f
     return f(*args, **kwargs)

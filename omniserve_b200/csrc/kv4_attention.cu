@@ -120,7 +120,83 @@ struct AttnParams {
   float* part_o; float* part_ml; int* counters;         // split-KV workspace
   int timestep;                                         // used when lengths == null
   int sub_chunk, eles_per_ind;                          // LServe page statistics (sparse op): 0 = none
+  // fused per-token INT8 quantisation of the attention output (extension): the last CTA of a sequence to finish
+  int8_t* q_out; __half* q_scale; __half* q_sum; int* tok_counters;   // quantises the [Hq*128] row; null = off
 };
+
+// invoke_quant(_fuse_sum) (fused_kernels.cu:57-142) of one attention-output row by the first 128 threads of the CTA,
+// with the element-to-thread assignment and reduction order of small_ops.cu:quant_kernel (bit-identical results).
+OB_DEVICE void quant_row_tail(const AttnParams& p, int b, float* red /*[64] shared*/) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int H = p.Hq * DH, nvec = H >> 3;
+  const __half* row = p.out + (size_t)b * H;
+  uint4 v[8];
+  float amax = 0.f, s = 0.f;
+  if (tid < 128) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 128;
+      if (idx < nvec) {
+        v[i] = __ldcg(reinterpret_cast<const uint4*>(row) + idx);
+        const __half* h = reinterpret_cast<const __half*>(&v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f = __half2float(h[j]);
+          s += f;
+          amax = fmaxf(amax, fabsf(f));
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, m));
+      s += __shfl_xor_sync(0xffffffffu, s, m);
+    }
+    if (lane == 0) { red[w] = amax; red[32 + w] = s; }
+  }
+  __syncthreads();
+  if (tid < 128) {
+    float x = lane < 4 ? red[lane] : -3.0e38f;
+    float y = lane < 4 ? red[32 + lane] : 0.f;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, m));
+      y += __shfl_xor_sync(0xffffffffu, y, m);
+    }
+    if (tid == 0) {
+      p.q_scale[b] = __float2half_rn(__fdividef(x, 127.0f));
+      if (p.q_sum) p.q_sum[b] = __float2half_rn(y);
+    }
+    const float qs = __fdividef(127.0f, x);
+    uint2* dst = reinterpret_cast<uint2*>(p.q_out + (size_t)b * H);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 128;
+      if (idx < nvec) {
+        const __half* h = reinterpret_cast<const __half*>(&v[i]);
+        uint32_t bq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bq[j] = (uint32_t)(uint8_t)f2i8_rni_sat(__half2float(h[j]) * qs);
+        uint2 r;
+        r.x = bq[0] | (bq[1] << 8) | (bq[2] << 16) | (bq[3] << 24);
+        r.y = bq[4] | (bq[5] << 8) | (bq[6] << 16) | (bq[7] << 24);
+        dst[idx] = r;
+      }
+    }
+  }
+}
+
+// Called by every thread of a CTA that has just written final outputs of sequence b.
+OB_DEVICE void fused_quant_tail(const AttnParams& p, int b, int* flag, float* red) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *flag = (atomicAdd(&p.tok_counters[b], 1) == (int)gridDim.y - 1);
+  __syncthreads();
+  if (!*flag) return;
+  __threadfence();
+  quant_row_tail(p, b, red);
+  if (threadIdx.x == 0) p.tok_counters[b] = 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Decode kernel.  160 threads: warps 0-3 compute, warp 4 = bulk-copy producer.
@@ -208,6 +284,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
   __shared__ float ml_s[4][8][2];
   __shared__ __align__(8) uint64_t full[V2_STAGES], empty[V2_STAGES];
   __shared__ int flag_s;
+  __shared__ float red_s[64];
 
   pdl_trigger();
   const int split = blockIdx.x;
@@ -559,7 +636,10 @@ kv4_decode_kernel(const AttnParams p, const int G) {
       if (d == 0) { p.part_ml[(slot * 8 + h) * 2] = M; p.part_ml[(slot * 8 + h) * 2 + 1] = den; }
     }
   }
-  if (p.n_split == 1) return;
+  if (p.n_split == 1) {
+    if (p.q_out) fused_quant_tail(p, b, &flag_s, red_s);
+    return;
+  }
   __threadfence();
   __syncthreads();
   const int cidx = b * gridDim.y + blockIdx.y;
@@ -581,6 +661,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
     p.out[((size_t)b * p.Hq + hq0 + h) * DH + d] = __float2half_rn(num * __fdividef(1.f, den + 1.e-6f));
   }
   if (tid == 0) p.counters[cidx] = 0;
+  if (p.q_out) fused_quant_tail(p, b, &flag_s, red_s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -722,8 +803,10 @@ static int ensure_att_ws(int dev, size_t slots, int G) {
   if (cudaMalloc(&g_part_ml[dev], need * 2 * 4) != cudaSuccess) return OB_ERR_CUDA;
   g_part_cap[dev] = need;
   if (!g_att_cnt[dev]) {
-    if (cudaMalloc(&g_att_cnt[dev], 65536 * 4) != cudaSuccess) return OB_ERR_CUDA;
-    cudaMemset(g_att_cnt[dev], 0, 65536 * 4);
+    // [0, 65536): split-KV arrival counters per (sequence, head group); [65536, 98304): per-sequence counters of the
+    // fused output quantisation
+    if (cudaMalloc(&g_att_cnt[dev], (65536 + 32768) * 4) != cudaSuccess) return OB_ERR_CUDA;
+    cudaMemset(g_att_cnt[dev], 0, (65536 + 32768) * 4);
     cudaDeviceSynchronize();
   }
   return 0;
@@ -754,6 +837,12 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
   p.rope_base = a.rotary_base; p.rope_scale = a.rotary_scale; p.rotary_dim = a.rotary_dim;
   p.timestep = a.timestep;
   p.sub_chunk = a.tokens_per_sub_chunk; p.eles_per_ind = a.hidden_dim_per_retrieval_token;
+  p.q_out = a.q_out; p.q_scale = a.q_scale; p.q_sum = a.q_sum; p.tok_counters = nullptr;
+  if (p.q_out) {
+    if (!p.q_scale || (a.Hq * DH) % 8 || (a.Hq * DH) / 8 > 8 * 128 || a.B > 32768) return OB_ERR_SHAPE;
+    if (int e = ensure_att_ws(dev, 1, 8)) return e;          // allocates the counter array (65536 ints) once
+    p.tok_counters = g_att_cnt[dev] + 65536;
+  }
   if (p.sub_chunk < 0 || (p.sub_chunk > 0 && TPB % p.sub_chunk)) return OB_ERR_SHAPE;
 
   // KV splits: enough CTAs to balance 148 SMs x ~4 resident CTAs, at least 4 pages per split

@@ -25,6 +25,7 @@ struct KV4DecodeArgs {
   int max_attended;                                    // upper bound of attended cached tokens per head
   int rotary_dim; float rotary_base; float rotary_scale;  // scale already inverted (1/factor)
   int force_split = 0;
+  int8_t* q_out = nullptr; __half* q_scale = nullptr; __half* q_sum = nullptr;   // fused output quant (extension)
   int tokens_per_sub_chunk = 0;                        // > 0: fold the appended key into the page's kmax / kmin
   int hidden_dim_per_retrieval_token = 0;
 };

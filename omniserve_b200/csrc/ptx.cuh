@@ -52,6 +52,25 @@ OB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// cluster-scope variants for barriers that CTAs of the same cluster arrive on remotely
+OB_DEVICE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of this cluster
+OB_DEVICE void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------ fences
 OB_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -115,6 +134,19 @@ OB_DEVICE void tmem_alloc(uint32_t* smem_slot) {
 template <uint32_t kCols>
 OB_DEVICE void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// cta_group::2 (CTA pair) variants: issued by the same warp of both CTAs with the same shared-memory slot offset.
+template <uint32_t kCols>
+OB_DEVICE void tmem_alloc2(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+OB_DEVICE void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
 // 16 lanes x 128 bit, repeated twice: thread t holds (lane t/4, col t%4), (lane t/4+8, col t%4),
@@ -193,6 +225,25 @@ OB_DEVICE void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// CTA-pair MMA (issued by one thread of the leader CTA, executes on both SMs): D[256 x N] (+)= A[256 x 32] * B[N x 32];
+// each CTA contributes its 128 rows of A (own tensor memory), N/2 rows of B (own shared memory, same offset) and
+// receives its 128 rows of D.
+OB_DEVICE void umma2_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Completion of all prior cta_group::2 MMAs -> arrive on the mbarrier at this offset in every CTA of `cta_mask`.
+OB_DEVICE void umma2_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
 // Same, arriving on the mbarrier at this offset in every CTA of `cta_mask`.
 OB_DEVICE void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(

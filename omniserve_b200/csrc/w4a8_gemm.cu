@@ -38,15 +38,18 @@ constexpr int W_STAGE = BM * BK / 2;  // 8192 packed bytes
 constexpr int NUM_THREADS = 384;
 constexpr int A_COLS_PER_STAGE = BK / 4;  // 32 TMEM columns hold 128 x 128 int8
 
-template <int BN>
+template <int BN, bool TWO = false>
 struct Cfg {
   // Three decoupled rings.  Packed weights come from HBM (long latency, nothing downstream holds them once they
   // are unpacked): deep ring, released by the unpack warps.  Activations come from L2 and the unpacked INT8
   // weights live in TMEM: shallow rings, released when the MMAs that read them retire.
-  static constexpr int W_STAGES = (BN >= 128) ? 6 : (BN >= 64 ? 12 : 16);
-  static constexpr int B_STAGES = (BN >= 128) ? 6 : 8;   // activation ring and TMEM A ring advance in lock-step:
-  static constexpr int A_SLOTS = B_STAGES;                 // one tcgen05.commit per K-block frees both
-  static constexpr int B_STAGE = BN * BK;
+  // TWO: CTA-pair MMA (tcgen05 cta_group::2, 256 weight rows x BN tokens per pair): each CTA stages only BN/2 token
+  // rows of the activation tile, so the bytes entering an SM per K-block drop from 8 KB + BN*128 to 8 KB + BN*64.
+  static constexpr int W_STAGES = TWO ? 8 : ((BN >= 128) ? 6 : (BN >= 64 ? 12 : 16));
+  static constexpr int B_STAGES = TWO ? 8 : ((BN >= 128) ? 6 : 8);   // activation ring and TMEM A ring advance in
+  static constexpr int A_SLOTS = B_STAGES;                             // lock-step: one commit per K-block frees both
+  static constexpr int B_ROWS = TWO ? BN / 2 : BN;       // token rows of the tile held by this CTA
+  static constexpr int B_STAGE = B_ROWS * BK;
   static constexpr int S2_STAGE = 256;
   static constexpr int ACC_BUFS = 2;
   static constexpr int TMEM_A_BASE = ACC_BUFS * BN;  // columns
@@ -183,11 +186,11 @@ OB_DEVICE uint32_t vadd4(uint32_t a, uint32_t b) {
   return s ^ ((a ^ b) & 0x80808080u);
 }
 
-template <int BN, bool PER_GROUP>
+template <int BN, bool PER_GROUP, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_constant__ CUtensorMap w_map,
                  const __grid_constant__ CUtensorMap act_mc_map, const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TWO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem + C::SMEM_B;
@@ -221,11 +224,16 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       uint64_t* b = bars + i;
       const bool four = (b >= w_empty && b < b_full) || (b >= a_full && b < ba_empty) || (b >= acc_empty);
       const bool mcb = (b >= b_empty_mc && b < acc_full);
-      mbar_init(b, mcb ? (uint32_t)p.mc : (four ? 4u : 1u));
+      uint32_t cnt = mcb ? (uint32_t)p.mc : (four ? 4u : 1u);
+      if (TWO) {
+        if (mcb) cnt = 1;                    // reused as peer_ready[]: the peer CTA's stage s (B half + A slot) is ready
+        if (b >= acc_empty) cnt = 8;         // leader: the epilogue warps of both CTAs drained the accumulator
+      }
+      mbar_init(b, cnt);
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == 2) { if (TWO) tmem_alloc2<C::TMEM_COLS>(tmem_slot); else tmem_alloc<C::TMEM_COLS>(tmem_slot); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -266,7 +274,16 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       KbIter it;
       it.init(p);
       int stage = 0, phase = 0;
-      if (p.mc > 1) {
+      if (TWO) {
+        // CTA pair: this CTA stages only its half of the token rows; the pair MMA reads both halves.
+        const int rank = (int)cluster_ctarank();
+        while (it.next(p)) {
+          mbar_wait_cluster(&ba_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&b_full[stage], C::B_STAGE);
+          tma_load_2d(sB + stage * C::B_STAGE, &act_mc_map, it.kb * BK, it.mt * BN + rank * C::B_ROWS, &b_full[stage]);
+          if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
+        }
+      } else if (p.mc > 1) {
         // Multicast: this CTA fetches rows [rank*BN/mc, (rank+1)*BN/mc) of the token tile and delivers them to every
         // CTA of the cluster (they work on different weight rows, same tokens, same K-block): L2 is read once per
         // cluster instead of once per CTA.  A stage may be refilled only when all mc CTAs have retired its MMAs.
@@ -298,9 +315,53 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     // one elected lane (elect.sync lets ptxas use plain uniform-register moves instead of a waterfall loop),
     // descriptors advanced by adds from loop-invariant bases, one commit per K-block.
     int st = 0, ph = 0, acc = 0, acc_phase = 0;
-    constexpr uint32_t idesc = umma_idesc_i8(BM, BN, true, true);
+    constexpr uint32_t idesc = umma_idesc_i8(TWO ? 2 * BM : BM, BN, true, true);
     const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(sB));
     const uint32_t a_tmem0 = tmem_base + C::TMEM_A_BASE;
+    if (TWO) {
+      uint64_t* peer_ready = b_empty_mc;
+      if (cluster_ctarank() == 0) {
+        // leader: issues the pair MMAs once its own stage and the peer's stage are both ready
+        while (it.next(sg)) {
+          mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+            mbar_wait(&b_full[st], ph);
+            mbar_wait(&a_full[st], ph);
+            mbar_wait_cluster(&peer_ready[st], ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t bdesc = bdesc0 + (uint64_t)((st * C::B_STAGE) >> 4);
+              const uint32_t a_tmem = a_tmem0 + st * A_COLS_PER_STAGE;
+              umma2_i8_ts(d_tmem, a_tmem, bdesc, idesc, kb > sg.kb0 ? 1u : 0u);
+              umma2_i8_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1u);
+              umma2_i8_ts(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1u);
+              umma2_i8_ts(d_tmem, a_tmem + 24, bdesc + 6, idesc, 1u);
+              umma2_commit_mc(&ba_empty[st], 3);                       // frees stage s in both CTAs
+              if (kb == sg.kb1 - 1) umma2_commit_mc(&acc_full[acc], 3);  // both epilogues may drain
+            }
+            __syncwarp();
+            if (++st == C::B_STAGES) { st = 0; ph ^= 1; }
+          }
+          if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+        }
+      } else {
+        // peer: forwards "my activation half landed and my TMEM A slot is filled" to the leader
+        while (it.next(sg)) {
+          for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+            mbar_wait(&b_full[st], ph);
+            mbar_wait(&a_full[st], ph);
+            tc_fence_after();
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive_remote(&peer_ready[st], 0);
+            __syncwarp();
+            if (++st == C::B_STAGES) { st = 0; ph ^= 1; }
+          }
+        }
+      }
+    } else
     while (it.next(sg)) {
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -371,7 +432,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[pending]);
         }
-        mbar_wait(&ba_empty[as], aph ^ 1);
+        if (TWO) mbar_wait_cluster(&ba_empty[as], aph ^ 1); else mbar_wait(&ba_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE + as * A_COLS_PER_STAGE;
         const uint32_t t_hi = t_lo + (16u << 16);
@@ -434,7 +495,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         sTok[et] = (m < p.M) ? __half2float(p.ascales[m]) : 0.f;
         sTok[BN + et] = (!PER_GROUP && m < p.M) ? __half2float(p.a_ssums[m]) : 0.f;
       }
-      mbar_wait(&acc_full[acc], acc_phase);
+      if (TWO) mbar_wait_cluster(&acc_full[acc], acc_phase); else mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       asm volatile("bar.sync 1, 128;" ::: "memory");  // sTok visible
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -490,7 +551,10 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) {
+        if (TWO && cluster_ctarank() != 0) mbar_arrive_remote(&acc_empty[acc], 0);
+        else mbar_arrive(&acc_empty[acc]);
+      }
       if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1; }
 
       if (full_tile) {
@@ -611,7 +675,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  if (warp == 2) { if (TWO) tmem_dealloc2<C::TMEM_COLS>(tmem_base); else tmem_dealloc<C::TMEM_COLS>(tmem_base); }
 }
 
 // ---------------------------------------------------------------------------------------------- host
@@ -703,11 +767,11 @@ static int ensure_workspace(int dev, int sms) {
   return 0;
 }
 
-template <int BN, bool PG>
+template <int BN, bool PG, bool TWO = false>
 static int launch(const CUtensorMap& map, const CUtensorMap& wmap, const CUtensorMap& mcmap, GemmParams& p, int grid,
                   unsigned cluster, cudaStream_t st) {
-  using C = Cfg<BN>;
-  auto kern = w4a8_gemm_kernel<BN, PG>;
+  using C = Cfg<BN, TWO>;
+  auto kern = w4a8_gemm_kernel<BN, PG, TWO>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL) != cudaSuccess)
@@ -761,6 +825,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   p.kb_per_tile = a.K / BK;
   const long long tiles = (long long)p.n_tiles * p.m_tiles;
   int grid;
+  int two = 0;
   unsigned cluster = 1;
   // Scheduling choice (cost model in K-block times, constants from tools/gemm_micro.py: the L2 bulk-reduce finalisation
   // of stream-K costs ~18 K-block times (0.27 us each)):
@@ -807,6 +872,11 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     int mc = 1;
     { const char* e3 = getenv("OB_GEMM_MC"); if (e3) mc = atoi(e3); }
     if (mc < 1 || mc > 4 || (mc & (mc - 1)) || p.n_tiles % mc || BN % (8 * mc) || a.force_ctas > 0) mc = 1;
+    // CTA-pair MMA (tcgen05 cta_group::2): 256 weight rows x 128 tokens per pair, each CTA stages half of the tokens.
+    // OB_GEMM_2CTA = 0 / 1 overrides the automatic choice (large-M data-parallel problems).
+    two = (BN == 128 && p.n_tiles % 2 == 0 && a.force_ctas <= 0 && tiles >= 4LL * sms) ? 1 : 0;
+    { const char* e4 = getenv("OB_GEMM_2CTA"); if (e4) two = (atoi(e4) != 0 && BN == 128 && p.n_tiles % 2 == 0 && a.force_ctas <= 0) ? 1 : 0; }
+    if (two) mc = 2;
     p.mc = mc;
     if (mc > 1) cluster = (unsigned)mc;
   }
@@ -827,7 +897,10 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     OB_LAUNCH(16)
     OB_LAUNCH(32)
     OB_LAUNCH(64)
-    OB_LAUNCH(128)
+    case 128:
+      if (two) return per_group ? launch<128, true, true>(map, wmap, mcmap, p, grid, cluster, st)
+                                : launch<128, false, true>(map, wmap, mcmap, p, grid, cluster, st);
+      return per_group ? launch<128, true>(map, wmap, mcmap, p, grid, cluster, st) : launch<128, false>(map, wmap, mcmap, p, grid, cluster, st);
     default:
       return OB_ERR_SHAPE;
   }

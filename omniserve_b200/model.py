@@ -175,6 +175,7 @@ class LlamaW4A8:
         self.inter = cfg.intermediate_size // tp_size
         self.fuse_silu_quant = fuse_silu_quant
         self.fuse_add_norm = hasattr(self.ops.layernorm_ops, "add_rms_norm_general")
+        self.fuse_attn_quant = hasattr(self.ops.fused_attention_pure_dense, "single_query_attention_quant")
         self.act_sum = cfg.group_size == -1
         gen = torch.Generator().manual_seed(seed * 1000 + tp_rank)
         gen_rep = torch.Generator().manual_seed(seed * 1000 + 999)  # replicated parameters: same on every rank
@@ -290,6 +291,7 @@ class LlamaW4A8:
         q3 = qkv[:, : self.q_size].view(T, self.hq, cfg.head_dim)
         k3 = qkv[:, self.q_size: self.q_size + self.kv_size].view(T, self.hkv, cfg.head_dim)
         v3 = qkv[:, self.q_size + self.kv_size:].view(T, self.hkv, cfg.head_dim)
+        attn_quant_done = False
         if is_prompt:
             # 3a. RoPE in place + KV4 page write, then fp16 flash attention (third party, llama:309-325)
             fused_attention_fine_grained_dense.apply_bias_rope_update_kv_cache(
@@ -298,13 +300,23 @@ class LlamaW4A8:
                 0, self.hkv, 0, cfg.head_dim, cfg.rope_theta, 1.0, 8192, True, True, True)
             attn = meta["prefill_attn"](q3, k3, v3).reshape(T, self.q_size)
         else:
-            # 3b. KV4 decode attention (decoding_attention.py:146-182)
-            attn = fused_attention_pure_dense.single_query_attention(
-                q3, k3, v3, self.kv.tables[li], meta["context_lens"], None, self.max_ctx, TOKENS_PER_BLOCK,
-                self.kv_size // 2, meta["timestep"], cfg.head_dim, cfg.rope_theta, True, True, True).reshape(T, self.q_size)
+            # 3b. KV4 decode attention (decoding_attention.py:146-182); with our ops the quant of step 4 is fused in
+            if self.fuse_attn_quant:
+                attn_quant_done = True
+                attn = fused_attention_pure_dense.single_query_attention_quant(
+                    q3, k3, v3, self.kv.tables[li], meta["context_lens"], None, self.max_ctx, TOKENS_PER_BLOCK,
+                    self.kv_size // 2, meta["timestep"], cfg.head_dim, cfg.rope_theta, True, True, True,
+                    b.quantized_attn_buffer[:T], b.quantized_sum_buffer[:T] if self.act_sum else None,
+                    b.quantized_scale_buffer[:T]).reshape(T, self.q_size)
+            else:
+                attn = fused_attention_pure_dense.single_query_attention(
+                    q3, k3, v3, self.kv.tables[li], meta["context_lens"], None, self.max_ctx, TOKENS_PER_BLOCK,
+                    self.kv_size // 2, meta["timestep"], cfg.head_dim, cfg.rope_theta, True, True, True).reshape(T, self.q_size)
         # 4. quant(+sum) of the attention output (llama:257-263,354)
         qa = b.quantized_attn_buffer[:T]
-        if self.act_sum:
+        if attn_quant_done:
+            pass
+        elif self.act_sum:
             fused_kernels.invoke_quant_fuse_sum(qa, attn, sm, sc)
         else:
             fused_kernels.invoke_quant(qa, attn, sc)
@@ -452,5 +464,5 @@ class DecodeGraph:
 
 def kernel_launches_per_decode_step(cfg: LlamaConfig, fuse_silu_quant: bool = True) -> int:
     """Count of OUR kernels launched per decode step (torch's embedding/add/matmul/argmax not included)."""
-    per_layer = 2 + 4 + 1 + 1 + (1 if fuse_silu_quant else 2)  # (add+)norms, gemms, attention, quant, silu(+quant)
+    per_layer = 2 + 4 + 1 + (1 if fuse_silu_quant else 2)  # (add+)norms, gemms, attention(+quant), silu(+quant)
     return per_layer * cfg.num_hidden_layers + 1  # + final (add+)rms_norm

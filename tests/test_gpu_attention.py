@@ -139,3 +139,37 @@ def test_append_then_read_roundtrip_property_long_context():
     torch.cuda.synchronize()
     assert not torch.equal(o1, o2)
     assert torch.isfinite(o2.float()).all()
+
+
+@pytest.mark.parametrize("force_split,with_sum", [(0, True), (3, True), (0, False), (2, False)])
+def test_fused_output_quant_equals_two_op_chain(force_split, with_sum):
+    """Extension: single_query_attention + invoke_quant(_fuse_sum) in one launch (the last CTA of a sequence quantises
+    its row).  Must be bit-identical to the reference's two-op chain (llama_w4a8_unpad.py:351-354) on the same pages."""
+    from omniserve_b200.backend import _attn_common as AC
+    from omniserve_b200.backend import fused_kernels
+    B, Hq, Hkv, lens = 5, 32, 8, (300, 70, 513, 64, 129)
+    cache, bt, q, k, v = make_kv_case(B, Hq, Hkv, lens, seed=11)
+    _, tq, tk, tv = qkv_views(q, k, v)
+    lens_t = t(np.asarray(lens, np.int32))
+    res = []
+    for fused in (False, True):
+        kpool, vpool, ptrs = device_tables(cache, bt)   # fresh copy of the pages for each variant
+        qo = torch.zeros((B, Hq * 128), dtype=torch.int8, device="cuda")
+        sc = torch.zeros((B,), dtype=torch.float16, device="cuda")
+        sm = torch.zeros((B,), dtype=torch.float16, device="cuda")
+        for rep in range(2):   # twice: the per-sequence counters must reset themselves
+            out = AC.single_query(tq, tk, tv, ptrs, None, None, None, None, lens_t, 64, Hkv, 0, 0, 0, 0, 0, max(lens) - 1, 128,
+                                  500000.0, 1.0, force_split=force_split,
+                                  quant=(qo, sc, sm if with_sum else None) if fused else None)
+            if not fused:
+                if with_sum:
+                    fused_kernels.invoke_quant_fuse_sum(qo, out.reshape(B, -1), sm, sc)
+                else:
+                    fused_kernels.invoke_quant(qo, out.reshape(B, -1), sc)
+            torch.cuda.synchronize()
+        res.append((out.cpu(), qo.cpu(), sc.cpu(), sm.cpu()))
+    (o0, q0, s0, m0), (o1, q1, s1, m1) = res
+    assert torch.equal(o0, o1) and torch.equal(q0, q1) and torch.equal(s0, s1)
+    if with_sum:
+        assert torch.equal(m0, m1)
+    assert q1.abs().max() == 127

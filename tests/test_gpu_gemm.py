@@ -135,13 +135,23 @@ def test_activation_multicast_clusters(mc, M, N, K, per_group, monkeypatch):
     assert run(M, N, K, per_group, seed=mc * 1000 + M, bn=128 if M > 64 else 0, mode=0) > 0.999
 
 
-def test_prefill_shape_multicast_matches_unicast(monkeypatch):
-    """M = 4096 tokens x a Llama-3-8B sized layer slice: multicast (auto) and unicast outputs are bit-identical
-    (INT32 accumulation is exact, the epilogue is per element)."""
+@pytest.mark.parametrize("per_group", [False, True])
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 1024), (128, 256, 512), (1000, 768, 2048), (129, 512, 128)])
+def test_cta_pair_mma(M, N, K, per_group, monkeypatch):
+    """Prefill path: tcgen05 cta_group::2 -- a pair of CTAs computes 256 weight rows x 128 tokens, each staging half of
+    the token rows.  Same results as the single-CTA kernel, including token tails and one-K-block problems."""
+    monkeypatch.setenv("OB_GEMM_2CTA", "1")
+    assert run(M, N, K, per_group, seed=M + N, bn=128, mode=0) > 0.999
+
+
+def test_prefill_shape_pair_and_multicast_match_single_cta(monkeypatch):
+    """M = 4096 tokens x a Llama-3-8B sized layer slice: CTA-pair (the automatic choice at this size), activation
+    multicast and plain single-CTA outputs are bit-identical (INT32 accumulation is exact, the epilogue is per element)."""
     from omniserve_b200 import _lib as L
     d = make_gemm_inputs(4096, 6144, 1024, 5)
     outs = []
-    for mc in ("1", "4", "2"):
+    for two, mc in (("0", "1"), ("1", "1"), ("0", "4"), ("0", "2")):
+        monkeypatch.setenv("OB_GEMM_2CTA", two)
         monkeypatch.setenv("OB_GEMM_MC", mc)
         out = torch.empty((4096, 6144), dtype=torch.float16, device="cuda")
         ta, tq, ts1, tsa, tsz, tss = (t(d[k]) for k in ("a", "qw", "s1", "sa", "szs", "ssum"))
@@ -149,4 +159,12 @@ def test_prefill_shape_multicast_matches_unicast(monkeypatch):
                                             4096, 6144, 1024, 6144, L.stream()) == 0
         torch.cuda.synchronize()
         outs.append(out.cpu())
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
+    monkeypatch.delenv("OB_GEMM_2CTA")
+    monkeypatch.delenv("OB_GEMM_MC")
+    out = torch.empty((4096, 6144), dtype=torch.float16, device="cuda")
+    assert L.lib().ob_w4a8_gemm_per_chn(L.ptr(ta), L.ptr(tq), L.ptr(ts1), L.ptr(tsa), L.ptr(tsz), L.ptr(tss), L.ptr(out),
+                                        4096, 6144, 1024, 6144, L.stream()) == 0     # automatic choice
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], out.cpu())

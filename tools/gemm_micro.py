@@ -47,6 +47,17 @@ def run(M, N, K, mode=-1, bn=0, ctas=0, tag=""):
           f"{by / us / 1e3:8.1f} GB/s  {2.0 * M * N * K / us / 1e6:8.1f} TOPS", flush=True)
 
 
+if __name__ == "__main__" and os.environ.get("OB_2CTA_EXP"):
+    for two in ("0", "1"):
+        os.environ["OB_GEMM_2CTA"] = two
+        run(8192, 6144, 4096, tag=f"prefill qkv 2cta={two}")
+        run(8192, 28672, 4096, tag=f"prefill gate_up 2cta={two}")
+        run(8192, 4096, 14336, tag=f"prefill down 2cta={two}")
+        run(8192, 4096, 4096, tag=f"prefill o 2cta={two}")
+        run(2048, 28672, 4096, tag=f"M=2048 gate_up 2cta={two}")
+        run(512, 28672, 4096, tag=f"M=512 gate_up 2cta={two}")
+    sys.exit(0)
+
 if __name__ == "__main__" and os.environ.get("OB_MC_EXP"):
     for mc in ("1", "2", "4"):
         os.environ["OB_GEMM_MC"] = mc
