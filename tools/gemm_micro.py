@@ -47,6 +47,13 @@ def run(M, N, K, mode=-1, bn=0, ctas=0, tag=""):
           f"{by / us / 1e3:8.1f} GB/s  {2.0 * M * N * K / us / 1e6:8.1f} TOPS", flush=True)
 
 
+if __name__ == "__main__" and os.environ.get("OB_2CTA_SWEEP"):
+    for two in ("0", "1"):
+        os.environ["OB_GEMM_2CTA"] = two
+        for M in (256, 512, 1024, 2048, 4096, 8192):
+            run(M, 6144, 4096, mode=0, bn=128, tag=f"qkv 2cta={two}")
+    sys.exit(0)
+
 if __name__ == "__main__" and os.environ.get("OB_2CTA_EXP"):
     for two in ("0", "1"):
         os.environ["OB_GEMM_2CTA"] = two
