@@ -278,7 +278,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         // CTA pair: this CTA stages only its half of the token rows; the pair MMA reads both halves.
         const int rank = (int)cluster_ctarank();
         while (it.next(p)) {
-          mbar_wait(&ba_empty[stage], phase ^ 1);
+          mbar_wait_cluster(&ba_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&b_full[stage], C::B_STAGE);
           tma_load_2d(sB + stage * C::B_STAGE, &act_mc_map, it.kb * BK, it.mt * BN + rank * C::B_ROWS, &b_full[stage]);
           if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
@@ -323,13 +323,13 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       if (cluster_ctarank() == 0) {
         // leader: issues the pair MMAs once its own stage and the peer's stage are both ready
         while (it.next(sg)) {
-          mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+          mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
           for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
             mbar_wait(&b_full[st], ph);
             mbar_wait(&a_full[st], ph);
-            mbar_wait(&peer_ready[st], ph);   // remote arrive has .release.cluster; the operands are async-proxy / TMEM state
+            mbar_wait_cluster(&peer_ready[st], ph);
             tc_fence_after();
             if (elect_one()) {
               const uint64_t bdesc = bdesc0 + (uint64_t)((st * C::B_STAGE) >> 4);
@@ -432,7 +432,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[pending]);
         }
-        mbar_wait(&ba_empty[as], aph ^ 1);
+        if (TWO) mbar_wait_cluster(&ba_empty[as], aph ^ 1); else mbar_wait(&ba_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE + as * A_COLS_PER_STAGE;
         const uint32_t t_hi = t_lo + (16u << 16);
@@ -495,7 +495,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         sTok[et] = (m < p.M) ? __half2float(p.ascales[m]) : 0.f;
         sTok[BN + et] = (!PER_GROUP && m < p.M) ? __half2float(p.a_ssums[m]) : 0.f;
       }
-      mbar_wait(&acc_full[acc], acc_phase);
+      if (TWO) mbar_wait_cluster(&acc_full[acc], acc_phase); else mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       asm volatile("bar.sync 1, 128;" ::: "memory");  // sTok visible
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;

@@ -135,6 +135,11 @@ def test_activation_multicast_clusters(mc, M, N, K, per_group, monkeypatch):
     assert run(M, N, K, per_group, seed=mc * 1000 + M, bn=128 if M > 64 else 0, mode=0) > 0.999
 
 
+_PAIR = pytest.mark.skipif(__import__("os").environ.get("OB_TEST_2CTA") != "1",
+                           reason="experimental CTA-pair kernel (opt-in, slower than the default): OB_TEST_2CTA=1")
+
+
+@_PAIR
 @pytest.mark.parametrize("per_group", [False, True])
 @pytest.mark.parametrize("M,N,K", [(300, 1024, 1024), (128, 256, 512), (1000, 768, 2048), (129, 512, 128)])
 def test_cta_pair_mma(M, N, K, per_group, monkeypatch):
@@ -150,7 +155,8 @@ def test_prefill_shape_pair_and_multicast_match_single_cta(monkeypatch):
     from omniserve_b200 import _lib as L
     d = make_gemm_inputs(4096, 6144, 1024, 5)
     outs = []
-    for two, mc in (("0", "1"), ("1", "1"), ("0", "4"), ("0", "2")):
+    pair = [("1", "1")] if __import__("os").environ.get("OB_TEST_2CTA") == "1" else []
+    for two, mc in [("0", "1")] + pair + [("0", "4"), ("0", "2")]:
         monkeypatch.setenv("OB_GEMM_2CTA", two)
         monkeypatch.setenv("OB_GEMM_MC", mc)
         out = torch.empty((4096, 6144), dtype=torch.float16, device="cuda")
