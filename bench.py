@@ -230,6 +230,9 @@ def prefill_gemm_tops(model, M=8192):
     return out
 
 
+# DRAM traffic per roofline unit from one `ncu --set full` capture per kernel (tools/ncu_targets.py, round 1):
+# the four decode GEMM launches of a layer: qkv 14.52 + o 9.79 + gate_up 59.48 + down 31.42 MB; attention 90.02 + 2.84 MB.
+NCU_DRAM_BYTES = {"w4a8_gemm(decode,4 launches/layer)": 115.2e6, "kv4_decode_attention": 92.9e6}
 INT8_PEAK_RECORDED = 4350.0  # TOPS, tools/umma_rate.cu on this pool's B200 (profiles/r1_umma_rate.log): 8188 MAC/clk/SM
 
 
@@ -468,7 +471,8 @@ def main():
     }
     dom = "w4a8_gemm(decode,4 launches/layer)" if gemm_ms >= kt["attention"] else "kv4_decode_attention"
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-            "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+            "frac": kernels[dom]["frac_hbm"], "traffic": NCU_DRAM_BYTES.get(dom), "peak_source": peak_src,
+            "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, cold launches (profiles/r1_ncu/*.raw.csv)",
             "share_of_step": cfg.num_hidden_layers * kernels[dom]["ms_per_layer"] / (ms / a.steps)}
     prefill = None
     if a.impl == "ours" and tp == 1 and not skip_prefill:

@@ -258,8 +258,10 @@ __global__ void __launch_bounds__(512) silu_and_mul_kernel(const __half* __restr
   }
 }
 
-template <bool FUSE_SUM>
-__global__ void __launch_bounds__(512) silu_mul_quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out,
+// NV = 16-byte vectors of the output row cached per thread (compile-time so that the register footprint -- and with
+// it the number of rows in flight per SM at prefill sizes -- follows the row length instead of the worst case).
+template <bool FUSE_SUM, int NV>
+__global__ void __launch_bounds__(512, (NV <= 4) ? 3 : 1) silu_mul_quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out,
                                       __half* __restrict__ scale, __half* __restrict__ sum, int d) {
   __shared__ float red[64];
   pdl_trigger();
@@ -268,10 +270,10 @@ __global__ void __launch_bounds__(512) silu_mul_quant_kernel(const __half* __res
   const int nvec = d >> 3;
   const uint4* g = reinterpret_cast<const uint4*>(in + row * 2 * d);
   const uint4* u = reinterpret_cast<const uint4*>(in + row * 2 * d + d);
-  V8 v[MAXV];
+  V8 v[NV];
   float amax = 0.f, s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
     if (idx < nvec) {
       V8 a, b;
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(512) silu_mul_quant_kernel(const __half* __res
   const float qs = __fdividef(127.0f, amax);
   uint2* dst = reinterpret_cast<uint2*>(out + row * d);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
     if (idx < nvec) {
       float f[8];
@@ -390,8 +392,13 @@ int silu_mul_quant_run(const __half* in, int8_t* out, __half* scale, __half* sum
   if (T <= 0) return 0;
   if (int e = check(d)) return e;
   const int th = pick_threads(d >> 3, 4);
-  cudaError_t e = sum ? launch_pdl(silu_mul_quant_kernel<true>, dim3(T), dim3(th), 0, st, in, out, scale, sum, d)
-                      : launch_pdl(silu_mul_quant_kernel<false>, dim3(T), dim3(th), 0, st, in, out, scale, (__half*)nullptr, d);
+  const int nv = ((d >> 3) + th - 1) / th;
+  cudaError_t e;
+#define OB_SILU(NVV)                                                                                              \
+  e = sum ? launch_pdl(silu_mul_quant_kernel<true, NVV>, dim3(T), dim3(th), 0, st, in, out, scale, sum, d)        \
+          : launch_pdl(silu_mul_quant_kernel<false, NVV>, dim3(T), dim3(th), 0, st, in, out, scale, (__half*)nullptr, d)
+  if (nv <= 1) { OB_SILU(1); } else if (nv <= 2) { OB_SILU(2); } else if (nv <= 4) { OB_SILU(4); } else { OB_SILU(8); }
+#undef OB_SILU
   return e == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
