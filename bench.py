@@ -272,6 +272,14 @@ def measure_tp(cfg, dev, rank, world, steps, warmup):
     torch.cuda.synchronize()
     per_chunk = sorted(x.elapsed_time(y) for x, y in chunk_ms)
     prefill_ms = sum(per_chunk[:-1]) * len(per_chunk) / max(1, len(per_chunk) - 1)
+    collective = "NCCL all-reduce (fp16 sum, [64, 4096]) after o_proj and after down_proj, inside the CUDA graph"
+    if os.environ.get("OB_PEER_ALLREDUCE", "1") != "0":
+        try:   # all-reduce fused into the following add+norm+quant kernel over NVLink peer memory
+            model.enable_peer_allreduce()
+            collective = ("all-reduce fused into the add+norm+quant kernel that consumes it: partial sums read from NVLink "
+                          "peer (symmetric) memory, per-block epoch flags, no NCCL call in the decode layers")
+        except Exception as e:  # symmetric memory unavailable: keep NCCL
+            print("peer all-reduce unavailable, using NCCL:", repr(e)[:200], file=sys.stderr)
     graph = DecodeGraph(model, max_ctx)
     graph.tokens.copy_(torch.cat(first))
     for _ in range(max(3, warmup)):
@@ -291,7 +299,7 @@ def measure_tp(cfg, dev, rank, world, steps, warmup):
     return {"value": BATCH * steps / (ms / 1e3), "unit": "tok/s", "ms_per_step": ms / steps, "steps": steps,
             "parallelism": f"tp{world}", "scaling": "strong", "global_batch": BATCH,
             "prefill_tok_per_s": BATCH * PROMPT_LEN / (prefill_ms / 1e3),
-            "collective": "NCCL all-reduce (fp16 sum, [64, 4096]) after o_proj and after down_proj, inside the CUDA graph"}
+            "collective": collective}
 
 
 def main():

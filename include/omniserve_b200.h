@@ -70,6 +70,24 @@ int ob_add_rms_norm_general(int8_t* out, const void* hidden_in, const void* delt
 int ob_add_rms_norm(void* out, const void* hidden_in, const void* delta, const void* weight, float eps, int num_tokens,
                     int hidden, void* stream);
 
+/* Extensions for tensor parallelism (the reference has none): the all-reduce that follows the row-parallel o_proj /
+ * down_proj is fused into the norm that consumes it.  Every rank's GEMM leaves its partial sums in a buffer that all
+ * GPUs of the node map (CUDA peer / symmetric memory over NVLink); the kernel exchanges per-block epoch flags in peer
+ * memory, sums the W partial rows in fp32 in rank order and continues as ob_add_rms_norm_general / ob_add_rms_norm.
+ * bufs[p] / flags[p]: rank p's buffer / flag array as mapped in THIS process (flags: uint32 [max_blocks][8], zeroed once;
+ * epoch: local uint32 [max_blocks], zeroed once).  num_tokens <= max_blocks; all ranks must call with the same shape. */
+typedef struct ob_peer_ctx {
+  const void* bufs[8];
+  void* flags[8];
+  void* epoch;
+  int world, rank, max_blocks;
+} ob_peer_ctx;
+int ob_peer_add_rms_norm_general(int8_t* out, const void* hidden_in, const ob_peer_ctx* peer, void* hidden_out,
+                                 const void* weight, void* input_sum, void* scaling, float eps, int num_tokens, int hidden,
+                                 void* stream);
+int ob_peer_add_rms_norm(void* out, const void* hidden_in, const ob_peer_ctx* peer, const void* weight, float eps,
+                         int num_tokens, int hidden, void* stream);
+
 /* ---- activation_ops.silu_and_mul (kernels/csrc/activation_kernels.cu:84-97); input [T,2d] -> out [T,d] */
 int ob_silu_and_mul(void* out, const void* input, int num_tokens, int d, void* stream);
 /* silu_and_mul fused with invoke_quant(_fuse_sum) (activation.py:54-77 runs them as two kernels);

@@ -53,6 +53,10 @@ class KV4PrefillArgs(C.Structure):
     ]
 
 
+class PeerCtx(C.Structure):
+    _fields_ = [("bufs", c_p * 8), ("flags", c_p * 8), ("epoch", c_p), ("world", c_i), ("rank", c_i), ("max_blocks", c_i)]
+
+
 class PageSelectorArgs(C.Structure):
     _fields_ = [
         ("q", c_p), ("q_batch_stride", c_ll), ("out", c_p),
@@ -79,6 +83,8 @@ _SIGS = {
     "ob_rms_norm_general_fuse_sum": ([c_p] * 5 + [c_f] + [c_i] * 2 + [c_p], c_i),
     "ob_add_rms_norm_general": ([c_p] * 7 + [c_f] + [c_i] * 2 + [c_p], c_i),
     "ob_add_rms_norm": ([c_p] * 4 + [c_f] + [c_i] * 2 + [c_p], c_i),
+    "ob_peer_add_rms_norm_general": ([c_p] * 2 + [C.POINTER(PeerCtx)] + [c_p] * 4 + [c_f] + [c_i] * 2 + [c_p], c_i),
+    "ob_peer_add_rms_norm": ([c_p] * 2 + [C.POINTER(PeerCtx)] + [c_p] + [c_f] + [c_i] * 2 + [c_p], c_i),
     "ob_silu_and_mul": ([c_p] * 2 + [c_i] * 2 + [c_p], c_i),
     "ob_silu_and_mul_quant": ([c_p] * 4 + [c_i] * 2 + [c_p], c_i),
     "ob_add_f16": ([c_p] * 3 + [c_ll] + [c_p], c_i),

@@ -56,5 +56,25 @@ def add_rms_norm(out, hidden_in, delta, weight, epsilon):
                                     L.stream()), "add_rms_norm")
 
 
+def peer_add_rms_norm_general(out, hidden_in, peer, hidden_out, weight, input_sum, scaling, epsilon):
+    """Extension for tensor parallelism: like add_rms_norm_general, but `delta` is the SUM over all ranks of the partial
+    results each rank's row-parallel GEMM left in `peer`'s symmetric buffer -- the all-reduce is done by this kernel over
+    NVLink peer memory (omniserve_b200/peer.py:PeerBuffer).  Collective: every rank must call it with the same shape."""
+    L.require_cuda(out, hidden_in, hidden_out, weight, input_sum, scaling)
+    T, H = _rows(hidden_in)
+    L.check(
+        L.lib().ob_peer_add_rms_norm_general(L.ptr(out), L.ptr(hidden_in), peer.ctx_ref(), L.ptr(hidden_out), L.ptr(weight),
+                                             L.ptr(input_sum), L.ptr(scaling), float(epsilon), T, H, L.stream()),
+        "peer_add_rms_norm_general")
+
+
+def peer_add_rms_norm(out, hidden_in, peer, weight, epsilon):
+    """Extension: rms_norm(out, hidden_in + all_reduce(partials in peer memory), weight, eps), fp16 out."""
+    L.require_cuda(out, hidden_in, weight)
+    T, H = _rows(hidden_in)
+    L.check(L.lib().ob_peer_add_rms_norm(L.ptr(out), L.ptr(hidden_in), peer.ctx_ref(), L.ptr(weight), float(epsilon), T, H,
+                                         L.stream()), "peer_add_rms_norm")
+
+
 def invoke_dequant_add_residual_rms_norm_quant(*a, **k):
     raise NotImplementedError("legacy W8A8 op, not on the W4A8KV4 path")

@@ -96,6 +96,25 @@ int ob_add_rms_norm(void* out, const void* hidden_in, const void* delta, const v
   if (!out || !hidden_in || !delta || !weight) return OB_ERR_ARG;
   return rmsnorm_f16_run(H(hidden_in), H(delta), H(weight), HM(out), T, Hd, eps, ST(stream));
 }
+static PeerArgs to_peer(const ob_peer_ctx* x) {
+  PeerArgs a{};
+  for (int p = 0; p < 8; ++p) { a.bufs[p] = H(x->bufs[p]); a.flags[p] = reinterpret_cast<uint32_t*>(x->flags[p]); }
+  a.epoch = reinterpret_cast<uint32_t*>(x->epoch); a.world = x->world; a.rank = x->rank; a.max_blocks = x->max_blocks;
+  return a;
+}
+int ob_peer_add_rms_norm_general(int8_t* out, const void* hidden_in, const ob_peer_ctx* peer, void* hidden_out,
+                                 const void* weight, void* input_sum, void* scaling, float eps, int T, int Hd, void* stream) {
+  if (T <= 0) return 0;
+  if (!out || !hidden_in || !peer || !hidden_out || !weight || !scaling) return OB_ERR_ARG;
+  return peer_rmsnorm_quant_run(H(hidden_in), to_peer(peer), HM(hidden_out), H(weight), out, HM(scaling), HM(input_sum), T, Hd,
+                                eps, ST(stream));
+}
+int ob_peer_add_rms_norm(void* out, const void* hidden_in, const ob_peer_ctx* peer, const void* weight, float eps, int T,
+                         int Hd, void* stream) {
+  if (T <= 0) return 0;
+  if (!out || !hidden_in || !peer || !weight) return OB_ERR_ARG;
+  return peer_rmsnorm_f16_run(H(hidden_in), to_peer(peer), H(weight), HM(out), T, Hd, eps, ST(stream));
+}
 int ob_silu_and_mul(void* out, const void* input, int T, int d, void* stream) {
   if (T <= 0) return 0;
   if (!out || !input) return OB_ERR_ARG;

@@ -57,6 +57,67 @@ OB_DEVICE uint2 pack8_i8(const float (&f)[8], float s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tensor-parallel all-reduce fused into the norm that consumes it (no reference counterpart: the reference has no
+// TP).  The row-parallel GEMM (o_proj / down_proj) of every rank leaves its partial sums in a symmetric buffer that
+// all GPUs of the node map over NVLink; the norm kernel of every rank then (1) tells its peers, block by block, that
+// its partials are complete and waits for theirs (monotonic epoch flags in peer memory, no reset, CUDA-graph safe),
+// (2) reads the W partial rows straight from peer memory, sums them in fp32 in rank order (identical result on every
+// rank) and (3) carries on as add + norm (+ quant) -- one kernel instead of NCCL all-reduce + add + norm + quant.
+// ------------------------------------------------------------------------------------------------
+struct PeerCtx {
+  const __half* bufs[8];   // rank p's partial sums [T, H], as mapped in this process
+  uint32_t* flags[8];      // rank p's flag array [blocks][8], as mapped in this process
+  uint32_t* epoch;         // local: calls made so far, per block
+  int world, rank;
+};
+
+OB_DEVICE void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+OB_DEVICE uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+OB_DEVICE uint4 ld_peer_v4(const void* p) {   // peer memory is not coherent with this SM's L1: bypass it
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+// Block b of every rank: "my partial sums are complete" -> all peers; wait for the same from all peers.  Must run after
+// griddepcontrol.wait (the producing GEMM of this rank has finished and flushed).
+OB_DEVICE void peer_barrier(const PeerCtx& c, uint32_t* e_s) {
+  if (threadIdx.x == 0) {
+    const uint32_t e = c.epoch[blockIdx.x] + 1;
+    c.epoch[blockIdx.x] = e;
+    *e_s = e;
+  }
+  __syncthreads();
+  const uint32_t e = *e_s;
+  if ((int)threadIdx.x < c.world) {
+    const int p = threadIdx.x;
+    st_release_sys_u32(c.flags[p] + blockIdx.x * 8 + c.rank, e);
+    while ((int)(ld_acquire_sys_u32(c.flags[c.rank] + blockIdx.x * 8 + p) - e) < 0) {
+    }
+  }
+  __syncthreads();
+}
+// fp32 sum over ranks 0..W-1 of the 8 halves at vector `idx` of `row`, rounded once to fp16
+OB_DEVICE uint4 peer_sum_v8(const PeerCtx& c, size_t row, int H, int idx) {
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int p = 0; p < c.world; ++p) {
+    V8 x;
+    x.u = ld_peer_v4(reinterpret_cast<const uint4*>(c.bufs[p] + row * H) + idx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __half2float(x.h[j]);
+  }
+  V8 r;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r.h[j] = __float2half_rn(acc[j]);
+  return r.u;
+}
+
+// ------------------------------------------------------------------------------------------------
 // invoke_quant / invoke_quant_fuse_sum   (fused_kernels.cu:57-142)
 // ------------------------------------------------------------------------------------------------
 template <bool FUSE_SUM>
@@ -107,12 +168,13 @@ __global__ void __launch_bounds__(512) quant_kernel(const __half* __restrict__ i
 // fp16-rounded before amax / sum, per-"reference thread" fp16 partial sums.  blockDim = refblock/8.
 // ------------------------------------------------------------------------------------------------
 // ADD: x = in + delta (fp16 add, like torch's residual add) is formed first and written to hidden_out.
-template <bool FUSE_SUM, bool ADD>
+template <bool FUSE_SUM, bool ADD, bool PEER = false>
 __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __restrict__ in, const __half* __restrict__ delta,
                                      __half* __restrict__ hidden_out, const __half* __restrict__ gamma,
                                      int8_t* __restrict__ out, __half* __restrict__ scale, __half* __restrict__ sum,
-                                     int H, float eps) {
+                                     int H, float eps, const PeerCtx pc) {
   __shared__ float red[64];
+  __shared__ uint32_t epoch_s;
   pdl_trigger();
   const size_t row = blockIdx.x;
   const int nvec = H >> 3;
@@ -121,6 +183,7 @@ __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __rest
   V8 v[MAXV];
   float s1 = 0.f, s2 = 0.f;
   pdl_wait();
+  if (PEER) peer_barrier(pc, &epoch_s);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
@@ -128,7 +191,8 @@ __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __rest
       v[i].u = ld_nc_v4(src + idx);
       if (ADD) {
         V8 dl;
-        dl.u = ld_nc_v4(reinterpret_cast<const uint4*>(delta + row * H) + idx);
+        if (PEER) dl.u = peer_sum_v8(pc, row, H, idx);
+        else dl.u = ld_nc_v4(reinterpret_cast<const uint4*>(delta + row * H) + idx);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[i].h2[j] = __hadd2(v[i].h2[j], dl.h2[j]);
         reinterpret_cast<uint4*>(hidden_out + row * H)[idx] = v[i].u;
@@ -185,10 +249,12 @@ __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __rest
 }
 
 // plain rms_norm, fp16 out (layernorm_kernels.cu:335-364): ((half)(x*rstd)) * w in half
-template <bool ADD>
+template <bool ADD, bool PEER = false>
 __global__ void __launch_bounds__(512) rmsnorm_f16_kernel(const __half* __restrict__ in, const __half* __restrict__ delta,
-                                   const __half* __restrict__ gamma, __half* __restrict__ out, int H, float eps) {
+                                   const __half* __restrict__ gamma, __half* __restrict__ out, int H, float eps,
+                                   const PeerCtx pc) {
   __shared__ float red[64];
+  __shared__ uint32_t epoch_s;
   pdl_trigger();
   const size_t row = blockIdx.x;
   const int nvec = H >> 3;
@@ -197,6 +263,7 @@ __global__ void __launch_bounds__(512) rmsnorm_f16_kernel(const __half* __restri
   V8 v[MAXV];
   float s2 = 0.f, dummy = 0.f;
   pdl_wait();
+  if (PEER) peer_barrier(pc, &epoch_s);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
@@ -204,7 +271,8 @@ __global__ void __launch_bounds__(512) rmsnorm_f16_kernel(const __half* __restri
       v[i].u = ld_nc_v4(src + idx);
       if (ADD) {
         V8 dl;
-        dl.u = ld_nc_v4(reinterpret_cast<const uint4*>(delta + row * H) + idx);
+        if (PEER) dl.u = peer_sum_v8(pc, row, H, idx);
+        else dl.u = ld_nc_v4(reinterpret_cast<const uint4*>(delta + row * H) + idx);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[i].h2[j] = __hadd2(v[i].h2[j], dl.h2[j]);
       }
@@ -362,11 +430,11 @@ int rmsnorm_quant_run(const __half* in, const __half* delta, __half* hidden_out,
   cudaError_t e;
   const dim3 g(T), b(th);
   if (delta) {
-    e = sum ? launch_pdl(rmsnorm_quant_kernel<true, true>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps)
-            : launch_pdl(rmsnorm_quant_kernel<false, true>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps);
+    e = sum ? launch_pdl(rmsnorm_quant_kernel<true, true>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, PeerCtx{})
+            : launch_pdl(rmsnorm_quant_kernel<false, true>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, PeerCtx{});
   } else {
-    e = sum ? launch_pdl(rmsnorm_quant_kernel<true, false>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps)
-            : launch_pdl(rmsnorm_quant_kernel<false, false>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps);
+    e = sum ? launch_pdl(rmsnorm_quant_kernel<true, false>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, PeerCtx{})
+            : launch_pdl(rmsnorm_quant_kernel<false, false>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, PeerCtx{});
   }
   return e == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
@@ -376,9 +444,47 @@ int rmsnorm_f16_run(const __half* in, const __half* delta, const __half* gamma, 
   if (T <= 0) return 0;
   if (int e = check(H)) return e;
   const dim3 g(T), b(pick_threads(H >> 3, 4));
-  cudaError_t e = delta ? launch_pdl(rmsnorm_f16_kernel<true>, g, b, 0, st, in, delta, gamma, out, H, eps)
-                        : launch_pdl(rmsnorm_f16_kernel<false>, g, b, 0, st, in, delta, gamma, out, H, eps);
+  cudaError_t e = delta ? launch_pdl(rmsnorm_f16_kernel<true>, g, b, 0, st, in, delta, gamma, out, H, eps, PeerCtx{})
+                        : launch_pdl(rmsnorm_f16_kernel<false>, g, b, 0, st, in, delta, gamma, out, H, eps, PeerCtx{});
   return e == cudaSuccess ? 0 : OB_ERR_CUDA;
+}
+
+static int fill_peer(PeerCtx& pc, const PeerArgs& a, int T) {
+  if (a.world < 2 || a.world > 8 || a.rank < 0 || a.rank >= a.world || !a.epoch || T > a.max_blocks) return OB_ERR_ARG;
+  for (int p = 0; p < a.world; ++p) {
+    if (!a.bufs[p] || !a.flags[p]) return OB_ERR_ARG;
+    pc.bufs[p] = a.bufs[p];
+    pc.flags[p] = a.flags[p];
+  }
+  pc.epoch = a.epoch; pc.world = a.world; pc.rank = a.rank;
+  return 0;
+}
+
+int peer_rmsnorm_quant_run(const __half* in, const PeerArgs& peer, __half* hidden_out, const __half* gamma, int8_t* out,
+                           __half* scale, __half* sum, int T, int H, float eps, cudaStream_t st) {
+  if (T <= 0) return 0;
+  int refblock = std::min(H, 1024);
+  refblock = 32 * ((refblock + 31) / 32);
+  if (int e = check(H, refblock / 8)) return e;
+  if (H % refblock != 0 && H > refblock) return OB_ERR_SHAPE;
+  PeerCtx pc{};
+  if (int e = fill_peer(pc, peer, T)) return e;
+  const dim3 g(T), b(std::max(32, refblock / 8));
+  const __half* nodelta = nullptr;
+  cudaError_t e = sum ? launch_pdl(rmsnorm_quant_kernel<true, true, true>, g, b, 0, st, in, nodelta, hidden_out, gamma, out, scale, sum, H, eps, pc)
+                      : launch_pdl(rmsnorm_quant_kernel<false, true, true>, g, b, 0, st, in, nodelta, hidden_out, gamma, out, scale, sum, H, eps, pc);
+  return e == cudaSuccess ? 0 : OB_ERR_CUDA;
+}
+
+int peer_rmsnorm_f16_run(const __half* in, const PeerArgs& peer, const __half* gamma, __half* out, int T, int H, float eps,
+                         cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (int e = check(H)) return e;
+  PeerCtx pc{};
+  if (int e = fill_peer(pc, peer, T)) return e;
+  const dim3 g(T), b(pick_threads(H >> 3, 4));
+  const __half* nodelta = nullptr;
+  return launch_pdl(rmsnorm_f16_kernel<true, true>, g, b, 0, st, in, nodelta, gamma, out, H, eps, pc) == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
 int silu_and_mul_run(const __half* in, __half* out, int T, int d, cudaStream_t st) {

@@ -200,6 +200,7 @@ class LlamaW4A8:
         self.lm_head = (torch.randn(self.vocab_local, H, generator=gen_v) * 0.02).half().to(device)
         self.kv: Optional[PagedKVCache] = None
         self.buf: Optional[ActivationBuffer] = None
+        self.peer = False
         # all heads are retrieval heads on the QServe dense path (ctx_attn_init.py:11-85)
         self._flags = torch.ones(self.hkv, dtype=torch.int32, device=device)
         self._rank = torch.arange(self.hkv, dtype=torch.int32, device=device)
@@ -255,12 +256,27 @@ class LlamaW4A8:
         if self.tp_size > 1:
             torch.distributed.all_reduce(t, group=self.pg)
 
+    def enable_peer_allreduce(self):
+        """Decode path, tp_size > 1: replace `NCCL all-reduce + add + norm + quant` after o_proj / down_proj by ONE kernel
+        that sums the ranks' partial results straight out of NVLink peer memory (csrc/small_ops.cu: PeerCtx).  Two
+        symmetric buffers alternate (o_proj -> A, down_proj -> B): a rank can only overwrite A after it has passed the
+        entry barrier of the next fused all-reduce on B, i.e. after every rank has finished reading A."""
+        from .peer import PeerGroup
+        assert self.tp_size > 1 and self.buf is not None
+        self.peer_group = PeerGroup(self.pg, self.device)
+        self.peer_a = self.peer_group.buffer(self.batch, self.cfg.hidden_size)
+        self.peer_b = self.peer_group.buffer(self.batch, self.cfg.hidden_size)
+        self.peer = True
+
     # ------------------------------------------------------------------ one decoder layer
     def _norm_quant(self, out_i8, hidden, delta, hidden_out, weight, sm, sc):
         """rms_norm_general(_fuse_sum) of (hidden [+ delta]).  With our ops the residual add of
         llama_w4a8_unpad.py:425,437 is fused into the norm (bit-identical to torch.add + norm); with the
         reference's ops it is a separate torch.add like in the reference.  Returns the tensor holding hidden+delta."""
         lo, eps = self.ops.layernorm_ops, self.cfg.rms_norm_eps
+        if delta is not None and not torch.is_tensor(delta):   # PeerBuffer: all-reduce fused into the norm
+            lo.peer_add_rms_norm_general(out_i8, hidden, delta, hidden_out, weight, sm if self.act_sum else None, sc, eps)
+            return hidden_out
         if delta is not None:
             if self.fuse_add_norm:
                 lo.add_rms_norm_general(out_i8, hidden, delta, hidden_out, weight, sm if self.act_sum else None, sc, eps)
@@ -320,11 +336,17 @@ class LlamaW4A8:
             fused_kernels.invoke_quant_fuse_sum(qa, attn, sm, sc)
         else:
             fused_kernels.invoke_quant(qa, attn, sc)
-        # 5. o_proj (row-parallel) -> all-reduce
-        ly["o_proj"](qa, sc, sm, od)
-        self._all_reduce(od)
+        # 5. o_proj (row-parallel) -> all-reduce (NCCL, or fused into the norm below over peer memory)
+        use_peer = self.peer and not is_prompt
+        if use_peer:
+            ly["o_proj"](qa, sc, sm, self.peer_a.tensor[:T])
+            od_attn = self.peer_a
+        else:
+            ly["o_proj"](qa, sc, sm, od)
+            self._all_reduce(od)
+            od_attn = od
         # 6-7. residual add + post_attention_layernorm
-        h2 = self._norm_quant(qh, h1, od, hb, ly["post_attention_layernorm"], sm, sc)
+        h2 = self._norm_quant(qh, h1, od_attn, hb, ly["post_attention_layernorm"], sm, sc)
         # 8-10. MLP (llama:83-112): gate_up -> silu*mul -> quant -> down (row-parallel) -> all-reduce
         gu = b.gate_up_proj_act_buffer[:T]
         ly["gate_up_proj"](qh, sc, sm, gu)
@@ -338,6 +360,9 @@ class LlamaW4A8:
                 fused_kernels.invoke_quant_fuse_sum(qm, tmp, sm, sc)
             else:
                 fused_kernels.invoke_quant(qm, tmp, sc)
+        if use_peer:
+            ly["down_proj"](qm, sc, sm, self.peer_b.tensor[:T])
+            return h2, self.peer_b  # the all-reduce and the add are folded into the next norm
         ly["down_proj"](qm, sc, sm, od)
         self._all_reduce(od)
         return h2, od  # the add of `od` is folded into the next norm
@@ -358,7 +383,9 @@ class LlamaW4A8:
     def _sample(self, hidden_last, delta=None):
         """final rms_norm (+ last residual add) + vocab-parallel lm_head + argmax (torch, as in the reference)."""
         x = torch.empty_like(hidden_last)
-        if delta is not None and self.fuse_add_norm:
+        if delta is not None and not torch.is_tensor(delta):
+            self.ops.layernorm_ops.peer_add_rms_norm(x, hidden_last, delta, self.norm_weight, self.cfg.rms_norm_eps)
+        elif delta is not None and self.fuse_add_norm:
             self.ops.layernorm_ops.add_rms_norm(x, hidden_last, delta, self.norm_weight, self.cfg.rms_norm_eps)
         else:
             if delta is not None:
