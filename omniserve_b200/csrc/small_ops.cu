@@ -71,6 +71,10 @@ struct PeerCtx {
   int world, rank;
 };
 
+struct NoPeer {};   // kernel-parameter placeholder of the non-TP instantiations (keeps their parameter block small)
+template <bool PEER> struct PeerSel { using type = NoPeer; };
+template <> struct PeerSel<true> { using type = PeerCtx; };
+
 OB_DEVICE void st_release_sys_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -172,7 +176,7 @@ template <bool FUSE_SUM, bool ADD, bool PEER = false>
 __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __restrict__ in, const __half* __restrict__ delta,
                                      __half* __restrict__ hidden_out, const __half* __restrict__ gamma,
                                      int8_t* __restrict__ out, __half* __restrict__ scale, __half* __restrict__ sum,
-                                     int H, float eps, const PeerCtx pc) {
+                                     int H, float eps, const typename PeerSel<PEER>::type pc) {
   __shared__ float red[64];
   __shared__ uint32_t epoch_s;
   pdl_trigger();
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __rest
   V8 v[MAXV];
   float s1 = 0.f, s2 = 0.f;
   pdl_wait();
-  if (PEER) peer_barrier(pc, &epoch_s);
+  if constexpr (PEER) peer_barrier(pc, &epoch_s);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __rest
       v[i].u = ld_nc_v4(src + idx);
       if (ADD) {
         V8 dl;
-        if (PEER) dl.u = peer_sum_v8(pc, row, H, idx);
+        if constexpr (PEER) dl.u = peer_sum_v8(pc, row, H, idx);
         else dl.u = ld_nc_v4(reinterpret_cast<const uint4*>(delta + row * H) + idx);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[i].h2[j] = __hadd2(v[i].h2[j], dl.h2[j]);
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __rest
 template <bool ADD, bool PEER = false>
 __global__ void __launch_bounds__(512) rmsnorm_f16_kernel(const __half* __restrict__ in, const __half* __restrict__ delta,
                                    const __half* __restrict__ gamma, __half* __restrict__ out, int H, float eps,
-                                   const PeerCtx pc) {
+                                   const typename PeerSel<PEER>::type pc) {
   __shared__ float red[64];
   __shared__ uint32_t epoch_s;
   pdl_trigger();
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(512) rmsnorm_f16_kernel(const __half* __restri
   V8 v[MAXV];
   float s2 = 0.f, dummy = 0.f;
   pdl_wait();
-  if (PEER) peer_barrier(pc, &epoch_s);
+  if constexpr (PEER) peer_barrier(pc, &epoch_s);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(512) rmsnorm_f16_kernel(const __half* __restri
       v[i].u = ld_nc_v4(src + idx);
       if (ADD) {
         V8 dl;
-        if (PEER) dl.u = peer_sum_v8(pc, row, H, idx);
+        if constexpr (PEER) dl.u = peer_sum_v8(pc, row, H, idx);
         else dl.u = ld_nc_v4(reinterpret_cast<const uint4*>(delta + row * H) + idx);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[i].h2[j] = __hadd2(v[i].h2[j], dl.h2[j]);
@@ -328,8 +332,10 @@ __global__ void __launch_bounds__(512) silu_and_mul_kernel(const __half* __restr
 
 // NV = 16-byte vectors of the output row cached per thread (compile-time so that the register footprint -- and with
 // it the number of rows in flight per SM at prefill sizes -- follows the row length instead of the worst case).
-template <bool FUSE_SUM, int NV>
-__global__ void __launch_bounds__(512, (NV <= 4) ? 3 : 1) silu_mul_quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out,
+// OCC3: cap registers for three resident CTAs per SM -- pays at prefill sizes (2.4 -> 4.5 TB/s at T = 8192), costs a few
+// spilled registers, so decode-sized launches (latency bound, 64 rows) use the uncapped instantiation.
+template <bool FUSE_SUM, int NV, bool OCC3>
+__global__ void __launch_bounds__(512, OCC3 ? 3 : 1) silu_mul_quant_kernel(const __half* __restrict__ in, int8_t* __restrict__ out,
                                       __half* __restrict__ scale, __half* __restrict__ sum, int d) {
   __shared__ float red[64];
   pdl_trigger();
@@ -430,11 +436,11 @@ int rmsnorm_quant_run(const __half* in, const __half* delta, __half* hidden_out,
   cudaError_t e;
   const dim3 g(T), b(th);
   if (delta) {
-    e = sum ? launch_pdl(rmsnorm_quant_kernel<true, true>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, PeerCtx{})
-            : launch_pdl(rmsnorm_quant_kernel<false, true>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, PeerCtx{});
+    e = sum ? launch_pdl(rmsnorm_quant_kernel<true, true>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, NoPeer{})
+            : launch_pdl(rmsnorm_quant_kernel<false, true>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, NoPeer{});
   } else {
-    e = sum ? launch_pdl(rmsnorm_quant_kernel<true, false>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, PeerCtx{})
-            : launch_pdl(rmsnorm_quant_kernel<false, false>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, PeerCtx{});
+    e = sum ? launch_pdl(rmsnorm_quant_kernel<true, false>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, NoPeer{})
+            : launch_pdl(rmsnorm_quant_kernel<false, false>, g, b, 0, st, in, delta, hidden_out, gamma, out, scale, sum, H, eps, NoPeer{});
   }
   return e == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
@@ -444,8 +450,8 @@ int rmsnorm_f16_run(const __half* in, const __half* delta, const __half* gamma, 
   if (T <= 0) return 0;
   if (int e = check(H)) return e;
   const dim3 g(T), b(pick_threads(H >> 3, 4));
-  cudaError_t e = delta ? launch_pdl(rmsnorm_f16_kernel<true>, g, b, 0, st, in, delta, gamma, out, H, eps, PeerCtx{})
-                        : launch_pdl(rmsnorm_f16_kernel<false>, g, b, 0, st, in, delta, gamma, out, H, eps, PeerCtx{});
+  cudaError_t e = delta ? launch_pdl(rmsnorm_f16_kernel<true>, g, b, 0, st, in, delta, gamma, out, H, eps, NoPeer{})
+                        : launch_pdl(rmsnorm_f16_kernel<false>, g, b, 0, st, in, delta, gamma, out, H, eps, NoPeer{});
   return e == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
@@ -500,10 +506,13 @@ int silu_mul_quant_run(const __half* in, int8_t* out, __half* scale, __half* sum
   const int th = pick_threads(d >> 3, 4);
   const int nv = ((d >> 3) + th - 1) / th;
   cudaError_t e;
-#define OB_SILU(NVV)                                                                                              \
-  e = sum ? launch_pdl(silu_mul_quant_kernel<true, NVV>, dim3(T), dim3(th), 0, st, in, out, scale, sum, d)        \
-          : launch_pdl(silu_mul_quant_kernel<false, NVV>, dim3(T), dim3(th), 0, st, in, out, scale, (__half*)nullptr, d)
-  if (nv <= 1) { OB_SILU(1); } else if (nv <= 2) { OB_SILU(2); } else if (nv <= 4) { OB_SILU(4); } else { OB_SILU(8); }
+#define OB_SILU(NVV, OCC)                                                                                              \
+  e = sum ? launch_pdl(silu_mul_quant_kernel<true, NVV, OCC>, dim3(T), dim3(th), 0, st, in, out, scale, sum, d)        \
+          : launch_pdl(silu_mul_quant_kernel<false, NVV, OCC>, dim3(T), dim3(th), 0, st, in, out, scale, (__half*)nullptr, d)
+  const bool big = T >= 1024;
+  if (nv <= 1) { OB_SILU(1, false); } else if (nv <= 2) { OB_SILU(2, false); }
+  else if (nv <= 4) { if (big) { OB_SILU(4, true); } else { OB_SILU(4, false); } }
+  else { OB_SILU(8, false); }
 #undef OB_SILU
   return e == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
