@@ -49,6 +49,18 @@ int ob_w4a8_gemm_ex(int per_group, const int8_t* in_feats, const int8_t* kernel,
                     const void* a_ssums, void* out_feats, int M, int N, int K, int ldc, int force_bn,
                     int force_mode, int force_ctas, void* stream);
 
+/* Extension (decode-sized M): the W4A8 GEMM followed, in the same launch, by the residual add + norm + per-token quant
+ * that consumes its output in the reference's layer (llama_w4a8_unpad.py:425-431: `residual + o_proj(...)` ->
+ * post_attention_layernorm -> int8; :437 + next layer's :416-421 for down_proj): hidden_out = hidden_in + out_feats
+ * (fp16), then as ob_rms_norm_general(_fuse_sum)(norm_out, hidden_out, norm_weight, ...).  out_feats is still written.
+ * ascales / a_ssums (inputs of the GEMM) may alias norm_scale / norm_sum (outputs of the tail).  Bit-identical to the
+ * three-op chain.  M <= 256, N <= 4096 (returns OB_ERR_SHAPE otherwise: call the ops separately). */
+int ob_w4a8_gemm_add_norm_quant(int per_group, const int8_t* in_feats, const int8_t* kernel, const int8_t* zeros,
+                                const int8_t* scales_i8, const void* wscales, const void* ascales, const void* w_szs,
+                                const void* a_ssums, void* out_feats, int M, int N, int K, int ldc, const void* hidden_in,
+                                void* hidden_out, const void* norm_weight, int8_t* norm_out, void* norm_sum,
+                                void* norm_scale, float eps, void* stream);
+
 /* ---- fused_kernels.invoke_quant / invoke_quant_fuse_sum (kernels/csrc/fused_kernels.cu:218-271), per-token */
 int ob_invoke_quant(int8_t* out, const void* input, void* scale, int num_tokens, int hidden, void* stream);
 int ob_invoke_quant_fuse_sum(int8_t* out, const void* input, void* input_sum, void* scale, int num_tokens,

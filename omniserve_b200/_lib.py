@@ -76,6 +76,7 @@ _SIGS = {
     "ob_w4a8_gemm_per_chn": ([c_p] * 7 + [c_i] * 4 + [c_p], c_i),
     "ob_w4a8_gemm_per_group": ([c_p] * 7 + [c_i] * 4 + [c_p], c_i),
     "ob_w4a8_gemm_ex": ([c_i] + [c_p] * 9 + [c_i] * 7 + [c_p], c_i),
+    "ob_w4a8_gemm_add_norm_quant": ([c_i] + [c_p] * 9 + [c_i] * 4 + [c_p] * 6 + [c_f] + [c_p], c_i),
     "ob_invoke_quant": ([c_p] * 3 + [c_i] * 2 + [c_p], c_i),
     "ob_invoke_quant_fuse_sum": ([c_p] * 4 + [c_i] * 2 + [c_p], c_i),
     "ob_rms_norm": ([c_p] * 3 + [c_f] + [c_i] * 2 + [c_p], c_i),

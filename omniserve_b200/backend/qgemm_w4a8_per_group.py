@@ -15,3 +15,23 @@ def gemm_forward_cuda(in_feats, kernel, zeros, scales_i8, wscales, ascales, out_
             L.ptr(in_feats), L.ptr(kernel), L.ptr(zeros), L.ptr(scales_i8), L.ptr(wscales), L.ptr(ascales),
             L.ptr(out_feats), M, N, K, ldc, L.stream()),
         "qgemm_w4a8_per_group.gemm_forward_cuda")
+
+
+def gemm_forward_cuda_add_norm_quant(in_feats, kernel, zeros, scales_i8, wscales, ascales, out_feats, hidden_in, hidden_out,
+                                     norm_weight, norm_out, norm_scale, epsilon):
+    """Extension: per-group GEMM + `hidden_in + out -> rms_norm_general -> int8` in one launch (see
+    qgemm_w4a8_per_chn.gemm_forward_cuda_add_norm_quant).  Returns False when the shape is outside the fused path."""
+    L.require_cuda(in_feats, kernel, zeros, scales_i8, wscales, ascales, out_feats, hidden_in, hidden_out, norm_weight, norm_out,
+                   norm_scale)
+    M, K = in_feats.shape[0], in_feats.shape[1]
+    N = out_feats.shape[-1]
+    if M > 256 or N > 4096 or not (hidden_in.is_contiguous() and hidden_out.is_contiguous() and norm_out.is_contiguous()):
+        return False
+    ldc = out_feats.stride(-2) if out_feats.dim() >= 2 else N
+    L.check(
+        L.lib().ob_w4a8_gemm_add_norm_quant(
+            1, L.ptr(in_feats), L.ptr(kernel), L.ptr(zeros), L.ptr(scales_i8), L.ptr(wscales), L.ptr(ascales), 0, 0,
+            L.ptr(out_feats), M, N, K, ldc, L.ptr(hidden_in), L.ptr(hidden_out), L.ptr(norm_weight), L.ptr(norm_out), 0,
+            L.ptr(norm_scale), float(epsilon), L.stream()),
+        "qgemm_w4a8_per_group.gemm_forward_cuda_add_norm_quant")
+    return True

@@ -41,6 +41,23 @@ int ob_w4a8_gemm_ex(int per_group, const int8_t* in_feats, const int8_t* kernel,
   return w4a8_gemm_run(a, per_group != 0, ST(stream));
 }
 
+int ob_w4a8_gemm_add_norm_quant(int per_group, const int8_t* in_feats, const int8_t* kernel, const int8_t* zeros,
+                                const int8_t* scales_i8, const void* wscales, const void* ascales, const void* w_szs,
+                                const void* a_ssums, void* out_feats, int M, int N, int K, int ldc, const void* hidden_in,
+                                void* hidden_out, const void* norm_weight, int8_t* norm_out, void* norm_sum,
+                                void* norm_scale, float eps, void* stream) {
+  if (!in_feats || !kernel || !wscales || !ascales || !out_feats) return OB_ERR_ARG;
+  if (per_group ? (!zeros || !scales_i8) : (!w_szs || !a_ssums)) return OB_ERR_ARG;
+  if (!hidden_in || !hidden_out || !norm_weight || !norm_out || !norm_scale) return OB_ERR_ARG;
+  W4A8GemmArgs a{};
+  a.in_feats = in_feats; a.qweight = kernel; a.s2_scales = scales_i8; a.s2_zeros = zeros;
+  a.wscales = H(wscales); a.ascales = H(ascales); a.w_szs = H(w_szs); a.a_ssums = H(a_ssums);
+  a.out_feats = HM(out_feats); a.M = M; a.N = N; a.K = K; a.ldc = ldc;
+  a.tail_hidden_in = H(hidden_in); a.tail_hidden_out = HM(hidden_out); a.tail_gamma = H(norm_weight);
+  a.tail_q = norm_out; a.tail_scale = HM(norm_scale); a.tail_sum = HM(norm_sum); a.tail_eps = eps;
+  return w4a8_gemm_run(a, per_group != 0, ST(stream));
+}
+
 int ob_w4a8_gemm_per_chn(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales,
                          const void* w_szs, const void* a_ssums, void* out_feats, int M, int N, int K, int ldc,
                          void* stream) {

@@ -21,6 +21,7 @@
 // that span CTAs are summed exactly in INT32 with cp.reduce.async.bulk (.add.s32) into an L2-resident
 // workspace and finished by the last contributor.
 #include "launch.h"
+#include "norm_tail.cuh"
 #include "ptx.cuh"
 #include "w4a8_gemm.h"
 
@@ -87,6 +88,13 @@ struct GemmParams {
   int mc;                   // mode 0: activation multicast across a cluster of mc N-tiles (1 = off)
   int units_per_cta;        // SK: K-blocks per CTA
   int group_m;              // DP raster: m-tiles per L2 group
+  // Optional tail (extension): once every tile of this GEMM is written, the epilogue warps of CTA r run the add + norm +
+  // quant(+sum) that consumes output row r (llama_w4a8_unpad.py:425-431,437 + next layer's :416-421) -- one launch and
+  // one grid-wide barrier instead of a kernel boundary.  tail = 0 off, 1 on.
+  int tail;
+  const __half* t_hidden_in; __half* t_hidden_out; const __half* t_gamma;
+  int8_t* t_q; __half* t_scale; __half* t_sum; float t_eps;
+  unsigned int* t_counter; unsigned int* t_gen;   // grid barrier (sense reversal), in the split-K counter workspace
   int w_rows2k;             // weight tensor map variant: 4 rows of 2 KB per K-block instead of 16 rows of 512 B
   int dbg;                  // timing experiments only (OB_GEMM_DBG): 1 = no wait::st, 2 = no unpack, 4 = no MMA
 };
@@ -667,6 +675,38 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // staging + sTok free for the next segment
     }
+    if (p.tail) {
+      // ---- grid-wide barrier among the epilogue warps (all CTAs are resident: grid <= #SMs, one CTA per SM), then
+      // ---- row r of the add+norm+quant by CTA r.  Other warps of the CTA are idle by now.
+      __shared__ float tail_red[64];
+      __threadfence();                                     // this CTA's output tiles are visible device-wide
+      tail_bar();
+      if (et == 0) {
+        unsigned int gen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(p.t_gen) : "memory");
+        if (atomicAdd(p.t_counter, 1u) == gridDim.x - 1) {
+          *p.t_counter = 0u;
+          __threadfence();
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.t_gen) : "memory");
+        } else {
+          unsigned int g2;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(p.t_gen) : "memory");
+          } while (g2 == gen);
+        }
+        __threadfence();
+      }
+      tail_bar();
+      for (int row = blockIdx.x; row < p.M; row += gridDim.x) {
+        const __half* drow = p.out + (size_t)row * p.ldc;
+        if (p.t_sum)
+          add_norm_quant_row<true>(et, p.t_hidden_in + (size_t)row * p.N, drow, p.t_hidden_out + (size_t)row * p.N, p.t_gamma,
+                                   p.t_q + (size_t)row * p.N, p.t_scale + row, p.t_sum + row, p.N, p.t_eps, tail_red);
+        else
+          add_norm_quant_row<false>(et, p.t_hidden_in + (size_t)row * p.N, drow, p.t_hidden_out + (size_t)row * p.N, p.t_gamma,
+                                    p.t_q + (size_t)row * p.N, p.t_scale + row, nullptr, p.N, p.t_eps, tail_red);
+      }
+    }
     if (p.mode == 2 && !cluster_done) cluster_barrier();
   }
   if (p.mode == 2 && warp < 8) cluster_barrier();  // non-epilogue warps: every thread of the cluster arrives once
@@ -760,9 +800,9 @@ static int ensure_workspace(int dev, int sms) {
   if (g_ws[dev]) return 0;
   size_t bytes = (size_t)sms * WS_INTS_PER_CTA * 4;
   if (cudaMalloc(&g_ws[dev], bytes) != cudaSuccess) return OB_ERR_CUDA;
-  if (cudaMalloc(&g_cnt[dev], sms * 4) != cudaSuccess) return OB_ERR_CUDA;
+  if (cudaMalloc(&g_cnt[dev], (sms + 2) * 4) != cudaSuccess) return OB_ERR_CUDA;   // + grid-barrier counter / generation
   cudaMemset(g_ws[dev], 0, bytes);
-  cudaMemset(g_cnt[dev], 0, sms * 4);
+  cudaMemset(g_cnt[dev], 0, (sms + 2) * 4);
   cudaDeviceSynchronize();
   return 0;
 }
@@ -819,6 +859,17 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   p.qweight = a.qweight; p.s2_scales = a.s2_scales; p.s2_zeros = a.s2_zeros;
   p.wscales = a.wscales; p.ascales = a.ascales; p.w_szs = a.w_szs; p.a_ssums = a.a_ssums;
   p.out = a.out_feats; p.ws = g_ws[dev]; p.counters = g_cnt[dev];
+  if (a.tail_hidden_in) {
+    // fused add + norm + quant tail: decode-sized M, rows of <= 4096 halves (4 vectors per tail thread), N == row length
+    if (a.M > 256 || a.N > TAIL_NV * TAIL_THREADS * 8 || (a.N & 7) || !a.tail_hidden_out || !a.tail_gamma || !a.tail_q ||
+        !a.tail_scale || a.force_mode == 2)
+      return OB_ERR_SHAPE;
+    p.tail = 1;
+    p.t_hidden_in = a.tail_hidden_in; p.t_hidden_out = a.tail_hidden_out; p.t_gamma = a.tail_gamma;
+    p.t_q = a.tail_q; p.t_scale = a.tail_scale; p.t_sum = a.tail_sum; p.t_eps = a.tail_eps;
+    p.t_counter = reinterpret_cast<unsigned int*>(g_cnt[dev] + g_num_sms);
+    p.t_gen = p.t_counter + 1;
+  }
   p.M = a.M; p.N = a.N; p.K = a.K; p.ldc = a.ldc;
   p.n_tiles = (a.N + BM - 1) / BM;
   p.m_tiles = (a.M + BN - 1) / BN;
@@ -876,6 +927,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     // OB_GEMM_2CTA = 0 / 1 overrides the automatic choice (large-M data-parallel problems).
     two = 0;  // opt-in until it beats the single-CTA kernel (profiles/r1_summary.md)
     { const char* e4 = getenv("OB_GEMM_2CTA"); if (e4) two = (atoi(e4) != 0 && BN == 128 && p.n_tiles % 2 == 0 && a.force_ctas <= 0) ? 1 : 0; }
+    if (p.tail) { two = 0; mc = 1; }   // the fused tail is only wired into the plain single-CTA schedule
     if (two) mc = 2;
     p.mc = mc;
     if (mc > 1) cluster = (unsigned)mc;

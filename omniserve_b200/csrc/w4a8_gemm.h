@@ -21,6 +21,14 @@ struct W4A8GemmArgs {
   int force_bn = 0;          // testing knobs: 0 = auto
   int force_mode = -1;       // -1 auto, 0 = data-parallel tiles, 1 = stream-K
   int force_ctas = 0;
+  // optional fused tail (extension): hidden_out = hidden_in + out_feats (fp16), then rms_norm_general(_fuse_sum) of it
+  const __half* tail_hidden_in = nullptr;   // [M, N]
+  __half* tail_hidden_out = nullptr;        // [M, N]
+  const __half* tail_gamma = nullptr;       // [N]
+  int8_t* tail_q = nullptr;                 // [M, N]
+  __half* tail_scale = nullptr;             // [M]
+  __half* tail_sum = nullptr;               // [M] or null
+  float tail_eps = 0.f;
 };
 
 int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st);

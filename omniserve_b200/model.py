@@ -107,6 +107,17 @@ class W4A8Linear:
             self.s2_zeros.copy_((-z * s2).to(torch.int8).to(dev))
         return self
 
+    def fused_add_norm_quant(self, x_i8, input_scales, input_sum, output_buffer, hidden_in, hidden_out, norm_weight, norm_out,
+                             norm_sum, norm_scale, eps) -> bool:
+        """GEMM + residual add + norm + quant in one launch (our ops only).  False -> not fusable, nothing launched."""
+        if self.per_channel:
+            f = getattr(self.ops.qgemm_w4a8_per_chn, "gemm_forward_cuda_add_norm_quant", None)
+            return bool(f) and f(x_i8, self.qweight, self.s1_scales, input_scales, self.s1_szeros, input_sum, output_buffer,
+                                 hidden_in, hidden_out, norm_weight, norm_out, norm_sum, norm_scale, eps)
+        f = getattr(self.ops.qgemm_w4a8_per_group, "gemm_forward_cuda_add_norm_quant", None)
+        return bool(f) and f(x_i8, self.qweight, self.s2_zeros, self.s2_scales, self.s1_scales, input_scales, output_buffer,
+                             hidden_in, hidden_out, norm_weight, norm_out, norm_scale, eps)
+
     def __call__(self, x_i8, input_scales, input_sum, output_buffer):
         if self.per_channel:  # forward_per_chn (w4a8_linear.py:109-123)
             self.ops.qgemm_w4a8_per_chn.gemm_forward_cuda(x_i8, self.qweight, self.s1_scales, input_scales, self.s1_szeros,
@@ -176,6 +187,10 @@ class LlamaW4A8:
         self.fuse_silu_quant = fuse_silu_quant
         self.fuse_add_norm = hasattr(self.ops.layernorm_ops, "add_rms_norm_general")
         self.fuse_attn_quant = hasattr(self.ops.fused_attention_pure_dense, "single_query_attention_quant")
+        # decode, tp_size == 1: `residual + o_proj/down_proj -> layernorm -> int8` as the tail of the GEMM launch
+        import os as _os
+        self.fuse_gemm_norm = (hasattr(self.ops.qgemm_w4a8_per_chn, "gemm_forward_cuda_add_norm_quant") and tp_size == 1
+                               and _os.environ.get("OB_FUSE_GEMM_NORM", "1") != "0")
         self.act_sum = cfg.group_size == -1
         gen = torch.Generator().manual_seed(seed * 1000 + tp_rank)
         gen_rep = torch.Generator().manual_seed(seed * 1000 + 999)  # replicated parameters: same on every rank
@@ -301,7 +316,12 @@ class LlamaW4A8:
         od = b.out_down_proj_act_buffer[:T]
         ha, hb = b.hidden_a[:T], b.hidden_b[:T]
         # 1. (residual add of the previous MLP +) input_layernorm -> int8 (+sum)  (llama:416-421, layernorm.py:86-101)
-        h1 = self._norm_quant(qh, hidden, delta, ha, ly["input_layernorm"], sm, sc)
+        if isinstance(delta, str):   # "done": the previous layer's down_proj launch already ran this norm as its tail
+            h1 = hidden
+        else:
+            h1 = self._norm_quant(qh, hidden, delta, ha, ly["input_layernorm"], sm, sc)
+        fuse_tail = self.fuse_gemm_norm and not is_prompt
+        eps = cfg.rms_norm_eps
         # 2. qkv_proj
         ly["qkv_proj"](qh, sc, sm, qkv)
         q3 = qkv[:, : self.q_size].view(T, self.hq, cfg.head_dim)
@@ -338,15 +358,19 @@ class LlamaW4A8:
             fused_kernels.invoke_quant(qa, attn, sc)
         # 5. o_proj (row-parallel) -> all-reduce (NCCL, or fused into the norm below over peer memory)
         use_peer = self.peer and not is_prompt
-        if use_peer:
-            ly["o_proj"](qa, sc, sm, self.peer_a.tensor[:T])
-            od_attn = self.peer_a
+        if fuse_tail and ly["o_proj"].fused_add_norm_quant(qa, sc, sm, od, h1, hb, ly["post_attention_layernorm"], qh,
+                                                            sm if self.act_sum else None, sc, eps):
+            h2 = hb   # 5-7 in one launch: o_proj, residual add, post_attention_layernorm, int8 quant
         else:
-            ly["o_proj"](qa, sc, sm, od)
-            self._all_reduce(od)
-            od_attn = od
-        # 6-7. residual add + post_attention_layernorm
-        h2 = self._norm_quant(qh, h1, od_attn, hb, ly["post_attention_layernorm"], sm, sc)
+            if use_peer:
+                ly["o_proj"](qa, sc, sm, self.peer_a.tensor[:T])
+                od_attn = self.peer_a
+            else:
+                ly["o_proj"](qa, sc, sm, od)
+                self._all_reduce(od)
+                od_attn = od
+            # 6-7. residual add + post_attention_layernorm
+            h2 = self._norm_quant(qh, h1, od_attn, hb, ly["post_attention_layernorm"], sm, sc)
         # 8-10. MLP (llama:83-112): gate_up -> silu*mul -> quant -> down (row-parallel) -> all-reduce
         gu = b.gate_up_proj_act_buffer[:T]
         ly["gate_up_proj"](qh, sc, sm, gu)
@@ -360,6 +384,9 @@ class LlamaW4A8:
                 fused_kernels.invoke_quant_fuse_sum(qm, tmp, sm, sc)
             else:
                 fused_kernels.invoke_quant(qm, tmp, sc)
+        if fuse_tail and li + 1 < cfg.num_hidden_layers and ly["down_proj"].fused_add_norm_quant(
+                qm, sc, sm, od, h2, ha, self.layers[li + 1]["input_layernorm"], qh, sm if self.act_sum else None, sc, eps):
+            return ha, "done"  # down_proj + residual add + the NEXT layer's input_layernorm + quant in one launch
         if use_peer:
             ly["down_proj"](qm, sc, sm, self.peer_b.tensor[:T])
             return h2, self.peer_b  # the all-reduce and the add are folded into the next norm
@@ -491,5 +518,7 @@ class DecodeGraph:
 
 def kernel_launches_per_decode_step(cfg: LlamaConfig, fuse_silu_quant: bool = True) -> int:
     """Count of OUR kernels launched per decode step (torch's embedding/add/matmul/argmax not included)."""
-    per_layer = 2 + 4 + 1 + (1 if fuse_silu_quant else 2)  # (add+)norms, gemms, attention(+quant), silu(+quant)
-    return per_layer * cfg.num_hidden_layers + 1  # + final (add+)rms_norm
+    # gemms (o_proj / down_proj carry the following add+norm+quant as their tail), attention(+quant), silu(+quant);
+    # stand-alone norms: layer 0's input_layernorm and the final (add+)rms_norm
+    per_layer = 4 + 1 + (1 if fuse_silu_quant else 2)
+    return per_layer * cfg.num_hidden_layers + 2

@@ -174,3 +174,42 @@ def test_prefill_shape_pair_and_multicast_match_single_cta(monkeypatch):
                                         4096, 6144, 1024, 6144, L.stream()) == 0     # automatic choice
     torch.cuda.synchronize()
     assert torch.equal(outs[0], out.cpu())
+
+
+@pytest.mark.parametrize("per_group,M,N,K", [(False, 64, 4096, 4096), (False, 64, 4096, 14336), (False, 3, 256, 512),
+                                             (True, 17, 1024, 1024), (False, 130, 2048, 1024), (True, 64, 4096, 4096)])
+def test_gemm_with_fused_add_norm_quant_tail(per_group, M, N, K):
+    """Extension: GEMM + `hidden + out -> rms_norm_general(_fuse_sum) -> int8` in ONE launch (grid barrier, then CTA r
+    finishes row r).  Every output must be bit-identical to the three-op chain, twice in a row (barrier state resets)."""
+    from omniserve_b200.backend import layernorm_ops, qgemm_w4a8_per_chn, qgemm_w4a8_per_group
+    d = make_gemm_inputs(M, N, K, seed=M + N + K, per_group=per_group)
+    rng = np.random.default_rng(1)
+    hidden = t(rng.standard_normal((M, N)).astype(np.float16))
+    gamma = t((1.0 + 0.1 * rng.standard_normal(N)).astype(np.float16))
+    ta, tq, ts1 = t(d["a"]), t(d["qw"]), t(d["s1"])
+
+    def buffers():
+        return dict(out=torch.zeros((M, N), dtype=torch.float16, device="cuda"), ho=torch.zeros((M, N), dtype=torch.float16, device="cuda"),
+                    q=torch.zeros((M, N), dtype=torch.int8, device="cuda"), sc=t(d["sa"]).clone(),
+                    sm=(t(d["ssum"]).clone() if not per_group else torch.zeros(M, dtype=torch.float16, device="cuda")))
+    c, f = buffers(), buffers()
+    # chain (scale / sum buffers are reused for the norm's outputs exactly like the model's activation arena)
+    if per_group:
+        qgemm_w4a8_per_group.gemm_forward_cuda(ta, tq, t(d["z2"]), t(d["s2"]), ts1, c["sc"], c["out"])
+        layernorm_ops.add_rms_norm_general(c["q"], hidden, c["out"], c["ho"], gamma, None, c["sc"], 1e-5)
+    else:
+        qgemm_w4a8_per_chn.gemm_forward_cuda(ta, tq, ts1, c["sc"], t(d["szs"]), c["sm"], c["out"])
+        layernorm_ops.add_rms_norm_general(c["q"], hidden, c["out"], c["ho"], gamma, c["sm"], c["sc"], 1e-5)
+    for rep in range(2):
+        f = buffers()
+        if per_group:
+            ok = qgemm_w4a8_per_group.gemm_forward_cuda_add_norm_quant(ta, tq, t(d["z2"]), t(d["s2"]), ts1, f["sc"], f["out"], hidden,
+                                                                       f["ho"], gamma, f["q"], f["sc"], 1e-5)
+        else:
+            ok = qgemm_w4a8_per_chn.gemm_forward_cuda_add_norm_quant(ta, tq, ts1, f["sc"], t(d["szs"]), f["sm"], f["out"], hidden,
+                                                                     f["ho"], gamma, f["q"], f["sm"], f["sc"], 1e-5)
+        torch.cuda.synchronize()
+        assert ok
+        for k in ("out", "ho", "q", "sc") + (() if per_group else ("sm",)):
+            assert torch.equal(c[k], f[k]), f"{k} differs (rep {rep})"
+    assert int(c["q"].abs().max()) == 127
