@@ -187,10 +187,12 @@ class LlamaW4A8:
         self.fuse_silu_quant = fuse_silu_quant
         self.fuse_add_norm = hasattr(self.ops.layernorm_ops, "add_rms_norm_general")
         self.fuse_attn_quant = hasattr(self.ops.fused_attention_pure_dense, "single_query_attention_quant")
-        # decode, tp_size == 1: `residual + o_proj/down_proj -> layernorm -> int8` as the tail of the GEMM launch
+        # decode, tp_size == 1: `residual + o_proj/down_proj -> layernorm -> int8` as the tail of the GEMM launch.  Opt-in
+        # (OB_FUSE_GEMM_NORM=1): bit-identical, but measured SLOWER than the PDL-chained separate norm kernel on B200
+        # (4.07 vs 3.99 ms per decode step, same box back to back) -- the grid-wide barrier costs more than the launch.
         import os as _os
         self.fuse_gemm_norm = (hasattr(self.ops.qgemm_w4a8_per_chn, "gemm_forward_cuda_add_norm_quant") and tp_size == 1
-                               and _os.environ.get("OB_FUSE_GEMM_NORM", "1") != "0")
+                               and _os.environ.get("OB_FUSE_GEMM_NORM", "0") == "1")
         self.act_sum = cfg.group_size == -1
         gen = torch.Generator().manual_seed(seed * 1000 + tp_rank)
         gen_rep = torch.Generator().manual_seed(seed * 1000 + 999)  # replicated parameters: same on every rank
@@ -518,7 +520,5 @@ class DecodeGraph:
 
 def kernel_launches_per_decode_step(cfg: LlamaConfig, fuse_silu_quant: bool = True) -> int:
     """Count of OUR kernels launched per decode step (torch's embedding/add/matmul/argmax not included)."""
-    # gemms (o_proj / down_proj carry the following add+norm+quant as their tail), attention(+quant), silu(+quant);
-    # stand-alone norms: layer 0's input_layernorm and the final (add+)rms_norm
-    per_layer = 4 + 1 + (1 if fuse_silu_quant else 2)
-    return per_layer * cfg.num_hidden_layers + 2
+    per_layer = 2 + 4 + 1 + (1 if fuse_silu_quant else 2)  # (add+)norms, gemms, attention(+quant), silu(+quant)
+    return per_layer * cfg.num_hidden_layers + 1  # + final (add+)rms_norm
