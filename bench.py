@@ -495,7 +495,10 @@ def main():
                      + BATCH * mid_ctx * model.hkv * 136 * cfg.num_hidden_layers) / hbm_peak / 1e6
     tp_result = None
     if use_dist and mode == "dp" and a.parallelism == "auto" and os.environ.get("OB_BENCH_TP", "1") != "0":
-        tp_result = measure_tp(cfg, dev, rank, world, min(a.steps, 64), a.warmup)
+        try:
+            tp_result = measure_tp(cfg, dev, rank, world, min(a.steps, 64), a.warmup)
+        except Exception as e:  # the headline (dp) measurement above stands on its own
+            tp_result = {"error": repr(e)[:300]}
 
     if rank != 0:
         return 0
