@@ -95,6 +95,7 @@ struct GemmParams {
   const __half* t_hidden_in; __half* t_hidden_out; const __half* t_gamma;
   int8_t* t_q; __half* t_scale; __half* t_sum; float t_eps;
   unsigned int* t_counter; unsigned int* t_gen;   // grid barrier (sense reversal), in the split-K counter workspace
+  long long* dbg_t;         // timing experiments only (OB_GEMM_DBGT = device address): [grid][16] wait cycles per role
   int w_rows2k;             // weight tensor map variant: 4 rows of 2 KB per K-block instead of 16 rows of 512 B
   int dbg;                  // timing experiments only (OB_GEMM_DBG): 1 = no wait::st, 2 = no unpack, 4 = no MMA
 };
@@ -188,6 +189,18 @@ OB_DEVICE void tile_coords(const GemmParams& p, int tile, int& nt, int& mt) {
   }
 }
 
+// Timing experiments: accumulate the cycles a role spends in a wait into tw[slot] when p.dbg_t is set.
+#define OB_TW(slot, call)                  \
+  do {                                     \
+    if (p.dbg_t) {                         \
+      const long long _t0 = clock64();     \
+      call;                                \
+      tw[slot] += clock64() - _t0;         \
+    } else {                               \
+      call;                                \
+    }                                      \
+  } while (0)
+
 // Bytewise (a + b) mod 256 on four packed bytes; `__vadd4` of the reference (per_group/gemm_cuda.cu:307).
 OB_DEVICE uint32_t vadd4(uint32_t a, uint32_t b) {
   uint32_t s = (a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu);
@@ -259,8 +272,10 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       KbIter it;
       it.init(p);
       int stage = 0, phase = 0;
+      long long tw[1] = {0};
+      const long long t_start = clock64();
       while (it.next(p)) {
-        mbar_wait(&w_empty[stage], phase ^ 1);
+        OB_TW(0, mbar_wait(&w_empty[stage], phase ^ 1));
         const int n_cnt = min(BM, p.N - it.nt * BM);
         mbar_arrive_expect_tx(&w_full[stage], ((p.dbg & 64) ? 0 : W_STAGE) + (PER_GROUP ? 2 * n_cnt : 0));
         if (!(p.dbg & 64)) {
@@ -273,6 +288,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         }
         if (++stage == C::W_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (p.dbg_t) { p.dbg_t[blockIdx.x * 16 + 0] = tw[0]; p.dbg_t[blockIdx.x * 16 + 9] = clock64() - t_start; }
     }
   } else if (warp == 3) {
     // ================================================================ activation producer (own warp: TMA issue
@@ -282,11 +298,12 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       KbIter it;
       it.init(p);
       int stage = 0, phase = 0;
+      long long tw[1] = {0};
       if (TWO) {
         // CTA pair: this CTA stages only its half of the token rows; the pair MMA reads both halves.
         const int rank = (int)cluster_ctarank();
         while (it.next(p)) {
-          mbar_wait_cluster(&ba_empty[stage], phase ^ 1);
+          OB_TW(0, mbar_wait_cluster(&ba_empty[stage], phase ^ 1));
           mbar_arrive_expect_tx(&b_full[stage], C::B_STAGE);
           tma_load_2d(sB + stage * C::B_STAGE, &act_mc_map, it.kb * BK, it.mt * BN + rank * C::B_ROWS, &b_full[stage]);
           if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
@@ -307,12 +324,13 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         }
       } else {
         while (it.next(p)) {
-          mbar_wait(&ba_empty[stage], phase ^ 1);
+          OB_TW(0, mbar_wait(&ba_empty[stage], phase ^ 1));
           mbar_arrive_expect_tx(&b_full[stage], (p.dbg & 32) ? 0 : C::B_STAGE);
           if (!(p.dbg & 32)) tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, it.mt * BN, &b_full[stage]);
           if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.dbg_t) p.dbg_t[blockIdx.x * 16 + 1] = tw[0];
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
@@ -326,18 +344,19 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     constexpr uint32_t idesc = umma_idesc_i8(TWO ? 2 * BM : BM, BN, true, true);
     const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(sB));
     const uint32_t a_tmem0 = tmem_base + C::TMEM_A_BASE;
+    long long tw[6] = {0, 0, 0, 0, 0, 0};
     if (TWO) {
       uint64_t* peer_ready = b_empty_mc;
       if (cluster_ctarank() == 0) {
         // leader: issues the pair MMAs once its own stage and the peer's stage are both ready
         while (it.next(sg)) {
-          mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
+          OB_TW(2, mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1));
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
           for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-            mbar_wait(&b_full[st], ph);
-            mbar_wait(&a_full[st], ph);
-            mbar_wait_cluster(&peer_ready[st], ph);
+            OB_TW(3, mbar_wait(&b_full[st], ph));
+            OB_TW(4, mbar_wait(&a_full[st], ph));
+            OB_TW(5, mbar_wait_cluster(&peer_ready[st], ph));
             tc_fence_after();
             if (elect_one()) {
               const uint64_t bdesc = bdesc0 + (uint64_t)((st * C::B_STAGE) >> 4);
@@ -358,8 +377,8 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         // peer: forwards "my activation half landed and my TMEM A slot is filled" to the leader
         while (it.next(sg)) {
           for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-            mbar_wait(&b_full[st], ph);
-            mbar_wait(&a_full[st], ph);
+            OB_TW(3, mbar_wait(&b_full[st], ph));
+            OB_TW(4, mbar_wait(&a_full[st], ph));
             tc_fence_after();
             tc_fence_before();
             __syncwarp();
@@ -371,12 +390,12 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       }
     } else
     while (it.next(sg)) {
-      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      OB_TW(2, mbar_wait(&acc_empty[acc], acc_phase ^ 1));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-        mbar_wait(&b_full[st], ph);
-        mbar_wait(&a_full[st], ph);
+        OB_TW(3, mbar_wait(&b_full[st], ph));
+        OB_TW(4, mbar_wait(&a_full[st], ph));
         tc_fence_after();
         if (elect_one()) {
           const uint64_t bdesc = bdesc0 + (uint64_t)((st * C::B_STAGE) >> 4);
@@ -396,6 +415,9 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       }
       if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.dbg_t && lane == 0) {
+      for (int i = 2; i < 6; ++i) p.dbg_t[blockIdx.x * 16 + i] = tw[i];
+    }
   } else if (warp >= 4 && warp < 8) {
     // ================================================================ INT4 -> INT8 unpack into TMEM
     const int q = warp - 4;  // TMEM lane quarter == n32 block inside the tile
@@ -407,10 +429,11 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     // per-K-block critical path of this warp (it was ~half of it).  a_full(i) is therefore signalled one iteration
     // late -- the 8-deep TMEM ring absorbs that -- and once more after the last K-block.
     int ws = 0, wph = 0, as = 0, aph = 0, pending = -1;
+    long long tw[2] = {0, 0};
     const uint32_t sW_u32 = smem_u32(sW), sS2_u32 = smem_u32(sS2);
     while (it.next(sg)) {
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-        mbar_wait(&w_full[ws], wph);
+        OB_TW(0, mbar_wait(&w_full[ws], wph));
         if (p.dbg & 2) {
           __syncwarp();
           if (lane == 0) { mbar_arrive(&w_empty[ws]); }
@@ -440,7 +463,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[pending]);
         }
-        if (TWO) mbar_wait_cluster(&ba_empty[as], aph ^ 1); else mbar_wait(&ba_empty[as], aph ^ 1);
+        if (TWO) OB_TW(1, mbar_wait_cluster(&ba_empty[as], aph ^ 1)); else OB_TW(1, mbar_wait(&ba_empty[as], aph ^ 1));
         tc_fence_after();
         const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE + as * A_COLS_PER_STAGE;
         const uint32_t t_hi = t_lo + (16u << 16);
@@ -473,6 +496,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[pending]);
     }
+    if (p.dbg_t && warp == 4 && lane == 0) { p.dbg_t[blockIdx.x * 16 + 6] = tw[0]; p.dbg_t[blockIdx.x * 16 + 7] = tw[1]; }
   } else if (warp >= 8) {
     // ================================================================ epilogue
     const int q = warp - 8;
@@ -484,6 +508,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     __half* stage16 = reinterpret_cast<__half*>(sStage);
     int32_t* stage32 = reinterpret_cast<int32_t*>(sStage);
     bool cluster_done = false;
+    long long tw[1] = {0};
     pdl_wait();  // ascales / a_ssums come from the previous kernel; `out` may still be read by it
     while (it.next(sg)) {
       int nt, mt;
@@ -503,7 +528,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         sTok[et] = (m < p.M) ? __half2float(p.ascales[m]) : 0.f;
         sTok[BN + et] = (!PER_GROUP && m < p.M) ? __half2float(p.a_ssums[m]) : 0.f;
       }
-      if (TWO) mbar_wait_cluster(&acc_full[acc], acc_phase); else mbar_wait(&acc_full[acc], acc_phase);
+      if (TWO) OB_TW(0, mbar_wait_cluster(&acc_full[acc], acc_phase)); else OB_TW(0, mbar_wait(&acc_full[acc], acc_phase));
       tc_fence_after();
       asm volatile("bar.sync 1, 128;" ::: "memory");  // sTok visible
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -675,6 +700,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // staging + sTok free for the next segment
     }
+    if (p.dbg_t && et == 0) p.dbg_t[blockIdx.x * 16 + 8] = tw[0];
     if (p.tail) {
       // ---- grid-wide barrier among the epilogue warps (all CTAs are resident: grid <= #SMs, one CTA per SM), then
       // ---- row r of the add+norm+quant by CTA r.  Other warps of the CTA are idle by now.
@@ -856,6 +882,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   if (a.force_bn > 0) BN = a.force_bn;
   GemmParams p{};
   { const char* e = getenv("OB_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("OB_GEMM_DBGT"); p.dbg_t = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr; }
   p.qweight = a.qweight; p.s2_scales = a.s2_scales; p.s2_zeros = a.s2_zeros;
   p.wscales = a.wscales; p.ascales = a.ascales; p.w_szs = a.w_szs; p.a_ssums = a.a_ssums;
   p.out = a.out_feats; p.ws = g_ws[dev]; p.counters = g_cnt[dev];
