@@ -69,7 +69,10 @@ OB_DEVICE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
 OB_DEVICE void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  // default semantics (.release at CTA scope) like cutlass::arch::ClusterBarrier::arrive(cta_id): the explicit
+  // .release.cluster form compiles to a heavy fence (ERRBAR) and made the per-K-block forwarding of the CTA-pair kernel
+  // its bottleneck (66 % of the leader's MMA warp time waiting, profiles/r1_gemm_role_waits.log)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------ fences
