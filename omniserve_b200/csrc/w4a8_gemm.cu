@@ -12,9 +12,8 @@
 // "lane" owns are exactly the four registers of a `tcgen05.st.16x128b.x2` fragment
 // (rows c / c+8, K-bytes 4e.. / 16+4e..), low nibbles = rows n, high nibbles = rows n+16.
 //
-// Warp roles (512 threads): w0 = weight TMA producer, w3 = activation TMA producer, w1 = MMA issuer, w2 = TMEM
-// allocator, w4-7 + w12-15 = INT4->INT8 unpack (+ level-2 q*s2+z for per-group) into the TMEM A ring (two warps per
-// TMEM lane quarter, each converting half of the K-block's columns),
+// Warp roles (384 threads): w0 = TMA/bulk producer, w1 = MMA issuer, w2 = TMEM allocator,
+// w4-7 = INT4->INT8 unpack (+ level-2 q*s2+z for per-group) into the TMEM A ring,
 // w8-11 = epilogue (TMEM -> regs -> fp32 math -> fp16 -> smem transpose -> 16 B global stores).
 //
 // Scheduling: persistent.  "DP" mode walks whole output tiles (prefill);  "SK" (stream-K) mode gives
@@ -37,7 +36,7 @@ namespace ob {
 constexpr int BM = 128;           // weight rows per tile  (UMMA M)
 constexpr int BK = 128;           // K bytes per pipeline stage (= one level-2 group)
 constexpr int W_STAGE = BM * BK / 2;  // 8192 packed bytes
-constexpr int NUM_THREADS = 512;   // 16 warps: see the role list in the header comment
+constexpr int NUM_THREADS = 384;
 constexpr int A_COLS_PER_STAGE = BK / 4;  // 32 TMEM columns hold 128 x 128 int8
 
 template <int BN, bool TWO = false>
@@ -244,10 +243,9 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     // one barrier per lane: arrival counts are 4 for the barriers the four unpack / epilogue warps arrive on
     for (int i = lane; i < C::NUM_BARS; i += 32) {
       uint64_t* b = bars + i;
-      const bool eight = (b >= w_empty && b < b_full) || (b >= a_full && b < ba_empty);   // the 8 unpack warps
-      const bool four = (b >= acc_empty);                                                  // the 4 epilogue warps
+      const bool four = (b >= w_empty && b < b_full) || (b >= a_full && b < ba_empty) || (b >= acc_empty);
       const bool mcb = (b >= b_empty_mc && b < acc_full);
-      uint32_t cnt = mcb ? (uint32_t)p.mc : (eight ? 8u : (four ? 4u : 1u));
+      uint32_t cnt = mcb ? (uint32_t)p.mc : (four ? 4u : 1u);
       if (TWO) {
         if (mcb) cnt = 1;                    // reused as peer_ready[]: the peer CTA's stage s (B half + A slot) is ready
         if (b >= acc_empty) cnt = 8;         // leader: the epilogue warps of both CTAs drained the accumulator
@@ -420,14 +418,9 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     if (p.dbg_t && lane == 0) {
       for (int i = 2; i < 6; ++i) p.dbg_t[blockIdx.x * 16 + i] = tw[i];
     }
-  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+  } else if (warp >= 4 && warp < 8) {
     // ================================================================ INT4 -> INT8 unpack into TMEM
-    // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31): warps 4-7 take the K-byte
-    // columns 0-63 of each K-block, warps 12-15 columns 64-127.  The per-K-block latency chain of an unpack warp
-    // (barrier wait -> ld.shared -> tcgen05.st) was the busiest role (78 % busy, MMA warp starved 31 % of the time:
-    // profiles/r1_gemm_role_waits.log); halving its work per K-block removes that limiter.
-    const int q = warp & 3;       // TMEM lane quarter == n32 block inside the tile
-    const int a0 = (warp >= 12) ? 2 : 0;   // first of the two 32-byte K-column groups this warp converts
+    const int q = warp - 4;  // TMEM lane quarter == n32 block inside the tile
     SegIter it;
     it.init(p);
     Seg sg;
@@ -451,9 +444,9 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
           continue;
         }
         const uint32_t wsm = sW_u32 + ws * W_STAGE + q * 2048 + lane * 16;
-        uint4 v[2];
+        uint4 v[4];
 #pragma unroll
-        for (int a = 0; a < 2; ++a) v[a] = lds_v4(wsm + (a0 + a) * 512);
+        for (int a = 0; a < 4; ++a) v[a] = lds_v4(wsm + a * 512);
         uint32_t sc[4], zr[4];
         if (PER_GROUP) {
           const uint32_t ps = lds_u32(sS2_u32 + ws * C::S2_STAGE + q * 32 + (lane >> 2) * 4);
@@ -475,7 +468,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE + as * A_COLS_PER_STAGE;
         const uint32_t t_hi = t_lo + (16u << 16);
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 4; ++a) {
           uint32_t l0 = v[a].x & 0x0F0F0F0Fu, l1 = v[a].y & 0x0F0F0F0Fu, l2 = v[a].z & 0x0F0F0F0Fu, l3 = v[a].w & 0x0F0F0F0Fu;
           uint32_t h0 = (v[a].x >> 4) & 0x0F0F0F0Fu, h1 = (v[a].y >> 4) & 0x0F0F0F0Fu, h2 = (v[a].z >> 4) & 0x0F0F0F0Fu,
                    h3 = (v[a].w >> 4) & 0x0F0F0F0Fu;
@@ -486,8 +479,8 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
             h0 = vadd4(h0 * sc[2], zr[2]); h2 = vadd4(h2 * sc[2], zr[2]);
             h1 = vadd4(h1 * sc[3], zr[3]); h3 = vadd4(h3 * sc[3], zr[3]);
           }
-          tmem_st_16x128b_x2(t_lo + (a0 + a) * 8, l0, l1, l2, l3);
-          tmem_st_16x128b_x2(t_hi + (a0 + a) * 8, h0, h1, h2, h3);
+          tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
+          tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
         }
         // the packed stage is in registers: hand it back to the producer right away
         __syncwarp();
@@ -504,7 +497,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       if (lane == 0) mbar_arrive(&a_full[pending]);
     }
     if (p.dbg_t && warp == 4 && lane == 0) { p.dbg_t[blockIdx.x * 16 + 6] = tw[0]; p.dbg_t[blockIdx.x * 16 + 7] = tw[1]; }
-  } else if (warp >= 8 && warp < 12) {
+  } else if (warp >= 8) {
     // ================================================================ epilogue
     const int q = warp - 8;
     const int et = threadIdx.x - 256;  // 0..127
@@ -742,7 +735,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     }
     if (p.mode == 2 && !cluster_done) cluster_barrier();
   }
-  if (p.mode == 2 && (warp < 8 || warp >= 12)) cluster_barrier();  // non-epilogue warps: every thread of the cluster arrives once
+  if (p.mode == 2 && warp < 8) cluster_barrier();  // non-epilogue warps: every thread of the cluster arrives once
   __syncwarp();
   if (p.mc > 1) cluster_barrier();  // peers may still multicast-arrive on this CTA's barriers until they are done too
 
