@@ -19,7 +19,7 @@ SOURCES = ["w4a8_gemm.cu", "small_ops.cu", "kv4_attention.cu", "lserve_ops.cu", 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--compiler-options", "-fPIC", "-Xptxas", "-v",
-]
+] + (["-DOB_GEMM_TIMING"] if os.environ.get("OB_GEMM_TIMING") == "1" else [])  # per-role wait counters (tools/gemm_waits.py)
 
 
 def _newest_src() -> float:

@@ -189,7 +189,10 @@ OB_DEVICE void tile_coords(const GemmParams& p, int tile, int& nt, int& mt) {
   }
 }
 
-// Timing experiments: accumulate the cycles a role spends in a wait into tw[slot] when p.dbg_t is set.
+// Timing experiments (compile with -DOB_GEMM_TIMING, run tools/gemm_waits.py): accumulate the cycles a role spends in a
+// wait into tw[slot] and dump them to p.dbg_t.  Compiled out by default: even disabled at run time the extra branches and
+// accumulators cost ~20 % of the kernel's throughput (measured, round 1).
+#ifdef OB_GEMM_TIMING
 #define OB_TW(slot, call)                  \
   do {                                     \
     if (p.dbg_t) {                         \
@@ -200,6 +203,13 @@ OB_DEVICE void tile_coords(const GemmParams& p, int tile, int& nt, int& mt) {
       call;                                \
     }                                      \
   } while (0)
+#define OB_TW_DECL(n) long long tw[n] = {}
+#define OB_TW_DUMP(stmt) do { if (p.dbg_t) { stmt; } } while (0)
+#else
+#define OB_TW(slot, call) call
+#define OB_TW_DECL(n) (void)0
+#define OB_TW_DUMP(stmt) (void)0
+#endif
 
 // Bytewise (a + b) mod 256 on four packed bytes; `__vadd4` of the reference (per_group/gemm_cuda.cu:307).
 OB_DEVICE uint32_t vadd4(uint32_t a, uint32_t b) {
@@ -272,8 +282,10 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       KbIter it;
       it.init(p);
       int stage = 0, phase = 0;
-      long long tw[1] = {0};
+      OB_TW_DECL(1);
+#ifdef OB_GEMM_TIMING
       const long long t_start = clock64();
+#endif
       while (it.next(p)) {
         OB_TW(0, mbar_wait(&w_empty[stage], phase ^ 1));
         const int n_cnt = min(BM, p.N - it.nt * BM);
@@ -288,7 +300,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         }
         if (++stage == C::W_STAGES) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg_t) { p.dbg_t[blockIdx.x * 16 + 0] = tw[0]; p.dbg_t[blockIdx.x * 16 + 9] = clock64() - t_start; }
+      OB_TW_DUMP(p.dbg_t[blockIdx.x * 16 + 0] = tw[0]; p.dbg_t[blockIdx.x * 16 + 9] = clock64() - t_start);
     }
   } else if (warp == 3) {
     // ================================================================ activation producer (own warp: TMA issue
@@ -298,7 +310,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       KbIter it;
       it.init(p);
       int stage = 0, phase = 0;
-      long long tw[1] = {0};
+      OB_TW_DECL(1);
       if (TWO) {
         // CTA pair: this CTA stages only its half of the token rows; the pair MMA reads both halves.
         const int rank = (int)cluster_ctarank();
@@ -330,7 +342,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
           if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.dbg_t) p.dbg_t[blockIdx.x * 16 + 1] = tw[0];
+      OB_TW_DUMP(p.dbg_t[blockIdx.x * 16 + 1] = tw[0]);
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
@@ -344,7 +356,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     constexpr uint32_t idesc = umma_idesc_i8(TWO ? 2 * BM : BM, BN, true, true);
     const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(sB));
     const uint32_t a_tmem0 = tmem_base + C::TMEM_A_BASE;
-    long long tw[6] = {0, 0, 0, 0, 0, 0};
+    OB_TW_DECL(6);
     if (TWO) {
       uint64_t* peer_ready = b_empty_mc;
       if (cluster_ctarank() == 0) {
@@ -415,9 +427,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       }
       if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.dbg_t && lane == 0) {
-      for (int i = 2; i < 6; ++i) p.dbg_t[blockIdx.x * 16 + i] = tw[i];
-    }
+    OB_TW_DUMP(if (lane == 0) for (int i = 2; i < 6; ++i) p.dbg_t[blockIdx.x * 16 + i] = tw[i]);
   } else if (warp >= 4 && warp < 8) {
     // ================================================================ INT4 -> INT8 unpack into TMEM
     const int q = warp - 4;  // TMEM lane quarter == n32 block inside the tile
@@ -429,7 +439,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     // per-K-block critical path of this warp (it was ~half of it).  a_full(i) is therefore signalled one iteration
     // late -- the 8-deep TMEM ring absorbs that -- and once more after the last K-block.
     int ws = 0, wph = 0, as = 0, aph = 0, pending = -1;
-    long long tw[2] = {0, 0};
+    OB_TW_DECL(2);
     const uint32_t sW_u32 = smem_u32(sW), sS2_u32 = smem_u32(sS2);
     while (it.next(sg)) {
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
@@ -496,7 +506,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[pending]);
     }
-    if (p.dbg_t && warp == 4 && lane == 0) { p.dbg_t[blockIdx.x * 16 + 6] = tw[0]; p.dbg_t[blockIdx.x * 16 + 7] = tw[1]; }
+    OB_TW_DUMP(if (warp == 4 && lane == 0) { p.dbg_t[blockIdx.x * 16 + 6] = tw[0]; p.dbg_t[blockIdx.x * 16 + 7] = tw[1]; });
   } else if (warp >= 8) {
     // ================================================================ epilogue
     const int q = warp - 8;
@@ -508,7 +518,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     __half* stage16 = reinterpret_cast<__half*>(sStage);
     int32_t* stage32 = reinterpret_cast<int32_t*>(sStage);
     bool cluster_done = false;
-    long long tw[1] = {0};
+    OB_TW_DECL(1);
     pdl_wait();  // ascales / a_ssums come from the previous kernel; `out` may still be read by it
     while (it.next(sg)) {
       int nt, mt;
@@ -700,7 +710,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // staging + sTok free for the next segment
     }
-    if (p.dbg_t && et == 0) p.dbg_t[blockIdx.x * 16 + 8] = tw[0];
+    OB_TW_DUMP(if (et == 0) p.dbg_t[blockIdx.x * 16 + 8] = tw[0]);
     if (p.tail) {
       // ---- grid-wide barrier among the epilogue warps (all CTAs are resident: grid <= #SMs, one CTA per SM), then
       // ---- row r of the add+norm+quant by CTA r.  Other warps of the CTA are idle by now.

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Where do the warp roles of the W4A8 GEMM wait?  Runs one prefill-shaped launch per variant with OB_GEMM_DBGT set and
-prints, per role, the cycles spent inside mbarrier waits (mean over CTAs; leader / peer separately for the CTA pair)."""
+prints, per role, the cycles spent inside mbarrier waits (mean over CTAs; leader / peer separately for the CTA pair).
+Needs the instrumented build:  OB_GEMM_TIMING=1 python -m omniserve_b200.build --force  (the counters are compiled out of
+the product build: they cost ~20 % of the kernel's throughput even when disabled at run time)."""
 import os
 import sys
 
