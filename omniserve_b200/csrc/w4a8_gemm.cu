@@ -96,6 +96,7 @@ struct GemmParams {
   int8_t* t_q; __half* t_scale; __half* t_sum; float t_eps;
   unsigned int* t_counter; unsigned int* t_gen;   // grid barrier (sense reversal), in the split-K counter workspace
   long long* dbg_t;         // timing experiments only (OB_GEMM_DBGT = device address): [grid][16] wait cycles per role
+  int unpack2;              // unpack warps take two K-blocks per iteration when both have landed (OB_GEMM_UNPACK2, default 1)
   int w_rows2k;             // weight tensor map variant: 4 rows of 2 KB per K-block instead of 16 rows of 512 B
   int dbg;                  // timing experiments only (OB_GEMM_DBG): 1 = no wait::st, 2 = no unpack, 4 = no MMA
 };
@@ -435,14 +436,66 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     it.init(p);
     Seg sg;
     // Software pipelined: the TMEM stores of K-block i are only waited for (tcgen05.wait::st) while the packed
-    // bytes of K-block i+1 are already on their way from shared memory, so the store-completion latency is off the
-    // per-K-block critical path of this warp (it was ~half of it).  a_full(i) is therefore signalled one iteration
-    // late -- the 8-deep TMEM ring absorbs that -- and once more after the last K-block.
-    int ws = 0, wph = 0, as = 0, aph = 0, pending = -1;
+    // bytes of the next K-block(s) are already on their way from shared memory, so the store-completion latency is off
+    // the per-K-block critical path of this warp.  a_full(i) is therefore signalled one iteration late -- the TMEM ring
+    // absorbs that -- and once more after the last K-block.
+    // Two K-blocks per iteration when the second one has already landed (never waited for): the role is a latency
+    // chain (mbarrier wait -> ld.shared -> tcgen05.st -> arrive; ~78 % busy with ~110 instructions per K-block,
+    // profiles/r1_gemm_role_waits.log), and pairing K-blocks halves the number of chain traversals.
+    int ws = 0, wph = 0, as = 0, aph = 0, pend0 = -1, pend1 = -1;
     OB_TW_DECL(2);
     const uint32_t sW_u32 = smem_u32(sW), sS2_u32 = smem_u32(sS2);
+    const uint32_t t_q = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE;
+
+    auto load_stage = [&](int st, uint4 (&v)[4]) {
+      const uint32_t wsm = sW_u32 + st * W_STAGE + q * 2048 + lane * 16;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) v[a] = lds_v4(wsm + a * 512);
+    };
+    auto convert_store = [&](int st, int slot, const uint4 (&v)[4]) {
+      uint32_t sc[4], zr[4];
+      if (PER_GROUP) {
+        const uint32_t ps = lds_u32(sS2_u32 + st * C::S2_STAGE + q * 32 + (lane >> 2) * 4);
+        const uint32_t pz = lds_u32(sS2_u32 + st * C::S2_STAGE + 128 + q * 32 + (lane >> 2) * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sc[j] = (ps >> (8 * j)) & 0xFFu;
+          zr[j] = ((pz >> (8 * j)) & 0xFFu) * 0x01010101u;
+        }
+      }
+      const uint32_t t_lo = t_q + slot * A_COLS_PER_STAGE;
+      const uint32_t t_hi = t_lo + (16u << 16);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        uint32_t l0 = v[a].x & 0x0F0F0F0Fu, l1 = v[a].y & 0x0F0F0F0Fu, l2 = v[a].z & 0x0F0F0F0Fu, l3 = v[a].w & 0x0F0F0F0Fu;
+        uint32_t h0 = (v[a].x >> 4) & 0x0F0F0F0Fu, h1 = (v[a].y >> 4) & 0x0F0F0F0Fu, h2 = (v[a].z >> 4) & 0x0F0F0F0Fu,
+                 h3 = (v[a].w >> 4) & 0x0F0F0F0Fu;
+        if (PER_GROUP) {
+          // rows: l0,l2 -> c (scale 0); l1,l3 -> c+8 (scale 1); h0,h2 -> c+16 (scale 2); h1,h3 -> c+24 (scale 3)
+          l0 = vadd4(l0 * sc[0], zr[0]); l2 = vadd4(l2 * sc[0], zr[0]);
+          l1 = vadd4(l1 * sc[1], zr[1]); l3 = vadd4(l3 * sc[1], zr[1]);
+          h0 = vadd4(h0 * sc[2], zr[2]); h2 = vadd4(h2 * sc[2], zr[2]);
+          h1 = vadd4(h1 * sc[3], zr[3]); h3 = vadd4(h3 * sc[3], zr[3]);
+        }
+        tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
+        tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
+      }
+    };
+    auto flush_pending = [&]() {
+      if (pend0 >= 0) {   // previous K-block(s): their TMEM stores have had a whole iteration to land
+        if (!(p.dbg & 1)) tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_full[pend0]);
+          if (pend1 >= 0) mbar_arrive(&a_full[pend1]);
+        }
+        pend0 = pend1 = -1;
+      }
+    };
+
     while (it.next(sg)) {
-      for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+      for (int kb = sg.kb0; kb < sg.kb1;) {
         OB_TW(0, mbar_wait(&w_full[ws], wph));
         if (p.dbg & 2) {
           __syncwarp();
@@ -451,61 +504,44 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
           if (lane == 0) { mbar_arrive(&a_full[as]); }
           if (++ws == C::W_STAGES) { ws = 0; wph ^= 1; }
           if (++as == C::A_SLOTS) { as = 0; aph ^= 1; }
+          ++kb;
           continue;
         }
-        const uint32_t wsm = sW_u32 + ws * W_STAGE + q * 2048 + lane * 16;
-        uint4 v[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) v[a] = lds_v4(wsm + a * 512);
-        uint32_t sc[4], zr[4];
-        if (PER_GROUP) {
-          const uint32_t ps = lds_u32(sS2_u32 + ws * C::S2_STAGE + q * 32 + (lane >> 2) * 4);
-          const uint32_t pz = lds_u32(sS2_u32 + ws * C::S2_STAGE + 128 + q * 32 + (lane >> 2) * 4);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sc[j] = (ps >> (8 * j)) & 0xFFu;
-            zr[j] = ((pz >> (8 * j)) & 0xFFu) * 0x01010101u;
-          }
+        int ws1 = ws + 1, wph1 = wph, as1 = as + 1, aph1 = aph;
+        if (ws1 == C::W_STAGES) { ws1 = 0; wph1 ^= 1; }
+        if (as1 == C::A_SLOTS) { as1 = 0; aph1 ^= 1; }
+        uint4 v0[4], v1[4];
+        load_stage(ws, v0);
+        // second K-block of the pair only if its bytes are already there (probe once, never wait)
+        bool two = false;
+        if (p.unpack2 && kb + 1 < sg.kb1) {
+          const int ready = (lane == 0) ? (int)mbar_test_wait(&w_full[ws1], wph1) : 0;
+          two = __shfl_sync(0xffffffffu, ready, 0) != 0;
         }
-        if (pending >= 0) {   // previous K-block: its TMEM stores have had a whole iteration to land
-          if (!(p.dbg & 1)) tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[pending]);
-        }
+        if (two) load_stage(ws1, v1);
+        flush_pending();
         OB_TW(1, mbar_wait(&ba_empty[as], aph ^ 1));
+        if (two) mbar_wait(&ba_empty[as1], aph1 ^ 1);
         tc_fence_after();
-        const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + C::TMEM_A_BASE + as * A_COLS_PER_STAGE;
-        const uint32_t t_hi = t_lo + (16u << 16);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          uint32_t l0 = v[a].x & 0x0F0F0F0Fu, l1 = v[a].y & 0x0F0F0F0Fu, l2 = v[a].z & 0x0F0F0F0Fu, l3 = v[a].w & 0x0F0F0F0Fu;
-          uint32_t h0 = (v[a].x >> 4) & 0x0F0F0F0Fu, h1 = (v[a].y >> 4) & 0x0F0F0F0Fu, h2 = (v[a].z >> 4) & 0x0F0F0F0Fu,
-                   h3 = (v[a].w >> 4) & 0x0F0F0F0Fu;
-          if (PER_GROUP) {
-            // rows: l0,l2 -> c (scale 0); l1,l3 -> c+8 (scale 1); h0,h2 -> c+16 (scale 2); h1,h3 -> c+24 (scale 3)
-            l0 = vadd4(l0 * sc[0], zr[0]); l2 = vadd4(l2 * sc[0], zr[0]);
-            l1 = vadd4(l1 * sc[1], zr[1]); l3 = vadd4(l3 * sc[1], zr[1]);
-            h0 = vadd4(h0 * sc[2], zr[2]); h2 = vadd4(h2 * sc[2], zr[2]);
-            h1 = vadd4(h1 * sc[3], zr[3]); h3 = vadd4(h3 * sc[3], zr[3]);
-          }
-          tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
-          tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
-        }
-        // the packed stage is in registers: hand it back to the producer right away
+        convert_store(ws, as, v0);
+        if (two) convert_store(ws1, as1, v1);
+        // the packed stage(s) are in registers: hand them back to the producer right away
         __syncwarp();
-        if (lane == 0) mbar_arrive(&w_empty[ws]);
-        pending = as;
+        if (lane == 0) {
+          mbar_arrive(&w_empty[ws]);
+          if (two) mbar_arrive(&w_empty[ws1]);
+        }
+        pend0 = as;
+        pend1 = two ? as1 : -1;
+        if (two) {
+          ws = ws1; wph = wph1; as = as1; aph = aph1;
+        }
         if (++ws == C::W_STAGES) { ws = 0; wph ^= 1; }
         if (++as == C::A_SLOTS) { as = 0; aph ^= 1; }
+        kb += two ? 2 : 1;
       }
     }
-    if (pending >= 0) {
-      if (!(p.dbg & 1)) tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[pending]);
-    }
+    flush_pending();
     OB_TW_DUMP(if (warp == 4 && lane == 0) { p.dbg_t[blockIdx.x * 16 + 6] = tw[0]; p.dbg_t[blockIdx.x * 16 + 7] = tw[1]; });
   } else if (warp >= 8) {
     // ================================================================ epilogue
@@ -892,6 +928,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   if (a.force_bn > 0) BN = a.force_bn;
   GemmParams p{};
   { const char* e = getenv("OB_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("OB_GEMM_UNPACK2"); p.unpack2 = e ? atoi(e) : 1; }
   { const char* e = getenv("OB_GEMM_DBGT"); p.dbg_t = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr; }
   p.qweight = a.qweight; p.s2_scales = a.s2_scales; p.s2_zeros = a.s2_zeros;
   p.wscales = a.wscales; p.ascales = a.ascales; p.w_szs = a.w_szs; p.a_ssums = a.a_ssums;
