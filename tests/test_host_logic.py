@@ -112,3 +112,26 @@ def test_tp_sharding_single_process_equivalence():
               @ w4a8.unpack_w4(rows[r]["qweight"].numpy()).astype(np.int64).T for r in range(size))
     np.testing.assert_array_equal(acc, full)
     assert tp.qkv_ranges(32, 8, 128, 1, 8) == [range(512, 1024), range(4096 + 128, 4096 + 256), range(5120 + 128, 5120 + 256)]
+
+
+def test_lserve_short_context_selects_every_page_in_order():
+    """decoding_attention.py:96-97: below the token budget every page is attended, newest last (no selector call)."""
+    import torch
+    from omniserve_b200 import lserve
+    cfg = lserve.SparseDecodeConfig(dynamic_sparse_token_budget=4096)
+    q = torch.zeros((2, 8, 128), dtype=torch.float16)
+    idx = lserve.dynamic_select_topk_pages(q, None, None, None, None, None, None, None, 0, 0, 0, 0, 2, 0, 130, cfg)
+    assert idx.dtype == torch.int32 and idx.shape == (2, 8, 3) and idx.is_contiguous()
+    assert idx[1, 5].tolist() == [0, 1, 2]
+
+
+def test_extension_entry_points_are_declared_and_exported():
+    """Every extension of the reference's op set is a C-ABI symbol declared in include/omniserve_b200.h."""
+    import os
+    from omniserve_b200 import _lib as L
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "omniserve_b200.h")).read()
+    for name in ("ob_w4a8_gemm_add_norm_quant", "ob_peer_add_rms_norm_general", "ob_peer_add_rms_norm", "ob_paged_min_max_pool",
+                 "ob_kv4_page_selector", "ob_silu_and_mul_quant", "ob_add_rms_norm_general", "ob_add_rms_norm"):
+        assert name in L.EXPORTS and f"int {name}(" in hdr
+    for name in L.EXPORTS:
+        assert name + "(" in hdr, f"{name} is bound by ctypes but not declared in the public header"
