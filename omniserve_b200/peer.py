@@ -28,14 +28,13 @@ class PeerGroup:
         self.rank = dist.get_rank(self.group)
         if not 2 <= self.world <= 8:
             raise RuntimeError("peer all-reduce supports 2..8 GPUs of one node")
-        if not getattr(symm, "is_symm_mem_enabled_for_group", lambda n: True)(self.group.group_name):
-            import warnings
-            with warnings.catch_warnings():   # a no-op (and deprecated) on recent PyTorch, required on older ones
-                warnings.simplefilter("ignore")
-                try:
-                    symm.enable_symm_mem_for_group(self.group.group_name)
-                except Exception:
-                    pass
+        import warnings
+        with warnings.catch_warnings():   # a no-op (and deprecated) on recent PyTorch, required on older ones
+            warnings.simplefilter("ignore")
+            try:
+                symm.enable_symm_mem_for_group(self.group.group_name)
+            except Exception:
+                pass
         self._symm = symm
         self.device = device
         self.flags = symm.empty(MAX_BLOCKS * 8, dtype=torch.int32, device=device)
