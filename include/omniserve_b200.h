@@ -139,6 +139,11 @@ typedef struct ob_kv4_decode_args {
    * off.  quant_out int8 [B, Hq*128], quant_scale fp16 [B], quant_sum fp16 [B] or NULL; bit-identical to the two-op
    * chain. */
   void* quant_out; void* quant_scale; void* quant_sum;
+  /* Extension: 1 = the caller guarantees that length_per_sample, the head / page tables, dynamic_sparse_page_idxes and
+   * every page except the newest were last written before the kernel that PRECEDES this call in the stream (true inside
+   * a decode loop); the kernel then streams those pages while its predecessor is still draining (programmatic dependent
+   * launch).  0 = read nothing before the stream dependency has resolved (safe right after a prefill write). */
+  int history_is_stable;
 } ob_kv4_decode_args;
 int ob_kv4_single_query_attention(const ob_kv4_decode_args* args, void* stream);
 

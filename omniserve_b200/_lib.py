@@ -37,6 +37,7 @@ class KV4DecodeArgs(C.Structure):
         ("force_split", c_i),
         ("tokens_per_sub_chunk", c_i), ("hidden_dim_per_retrieval_token", c_i),
         ("quant_out", c_p), ("quant_scale", c_p), ("quant_sum", c_p),
+        ("history_is_stable", c_i),
     ]
 
 
@@ -133,3 +134,10 @@ def require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise RuntimeError("omniserve_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def require_contiguous(*ts):
+    """The C ABI takes raw base pointers and dense row pitches: reject strided views instead of reading past them."""
+    for t in ts:
+        if t is not None and not t.is_contiguous():
+            raise RuntimeError("omniserve_b200: this op needs contiguous tensors (got a strided view)")

@@ -18,7 +18,7 @@ def _check_qkv(q, k, v):
 
 def single_query(q, k, v, r_tab, s_tab, flags, rank, dyn, lengths, tokens_per_block, n_r_heads, n_s_heads,
                  sink, local, sink_blk, local_blk, timestep, rot_dim, rot_base, rot_scale, force_split=0,
-                 tokens_per_sub_chunk=0, hidden_dim_per_retrieval_token=0, quant=None):
+                 tokens_per_sub_chunk=0, hidden_dim_per_retrieval_token=0, quant=None, history_is_stable=False):
     """quant = (out_i8 [B, Hq*Dh], scale fp16 [B], sum fp16 [B] or None): also quantise the output row per token."""
     _check_qkv(q, k, v)
     B, Hq, Dh = q.shape
@@ -47,6 +47,7 @@ def single_query(q, k, v, r_tab, s_tab, flags, rank, dyn, lengths, tokens_per_bl
     a.rotary_embedding_dim, a.rotary_base, a.rotary_scale = int(rot_dim), float(rot_base), float(rot_scale)
     a.force_split = force_split
     a.tokens_per_sub_chunk, a.hidden_dim_per_retrieval_token = int(tokens_per_sub_chunk), int(hidden_dim_per_retrieval_token)
+    a.history_is_stable = 1 if history_is_stable else 0
     if quant is not None:
         qo, qs, qsum = quant
         L.require_cuda(qo, qs, qsum)

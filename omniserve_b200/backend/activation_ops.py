@@ -4,6 +4,7 @@ from .. import _lib as L
 
 def silu_and_mul(out, input):
     L.require_cuda(out, input)
+    L.require_contiguous(out, input)
     d = input.shape[-1] // 2
     T = input.numel() // input.shape[-1]
     L.check(L.lib().ob_silu_and_mul(L.ptr(out), L.ptr(input), T, d, L.stream()), "silu_and_mul")
@@ -12,6 +13,7 @@ def silu_and_mul(out, input):
 def silu_and_mul_quant(out, input, input_sum, scale):
     """Extension (not in the reference): silu_and_mul fused with invoke_quant(_fuse_sum); input_sum may be None."""
     L.require_cuda(out, input, input_sum, scale)
+    L.require_contiguous(out, input, input_sum, scale)
     d = input.shape[-1] // 2
     T = input.numel() // input.shape[-1]
     L.check(

@@ -9,7 +9,7 @@ def single_query_attention(q, k, v, retrieval_kv_pointers, streaming_kv_pointers
                            head_rank_table, length_per_sample_, alibi_slopes_, memory_max_seqlen, tokens_per_block,
                            size_per_retrieval_token, size_per_streaming_token, sink_token_num, local_token_num,
                            sink_block_num, local_block_num, num_retrieval_kv_heads, num_streaming_kv_heads, timestep,
-                           rotary_embedding_dim, rotary_base, rotary_scale, neox_rotary_style, int4_kv_cache,
+                           rotary_embedding_dim, rotary_base, rotary_embedding_scale, neox_rotary_style, int4_kv_cache,
                            kv_cache_with_zeros, multiblock_switch):
     A._require_kv4(int4_kv_cache, kv_cache_with_zeros)
     if alibi_slopes_ is not None or not neox_rotary_style:
@@ -17,7 +17,7 @@ def single_query_attention(q, k, v, retrieval_kv_pointers, streaming_kv_pointers
     return A.single_query(q, k, v, retrieval_kv_pointers, streaming_kv_pointers, retrieval_head_flags,
                           head_rank_table, None, length_per_sample_, tokens_per_block, num_retrieval_kv_heads,
                           num_streaming_kv_heads, sink_token_num, local_token_num, sink_block_num, local_block_num,
-                          timestep, rotary_embedding_dim, rotary_base, rotary_scale)
+                          timestep, rotary_embedding_dim, rotary_base, rotary_embedding_scale)
 
 
 def apply_bias_rope_update_kv_cache(qkv, retrieval_seq_lens, streaming_seq_lens, padding_offset,

@@ -172,6 +172,7 @@ int ob_kv4_single_query_attention(const ob_kv4_decode_args* x, void* stream) {
   a.tokens_per_sub_chunk = x->tokens_per_sub_chunk;
   a.hidden_dim_per_retrieval_token = x->hidden_dim_per_retrieval_token;
   a.q_out = reinterpret_cast<int8_t*>(x->quant_out); a.q_scale = HM(x->quant_scale); a.q_sum = HM(x->quant_sum);
+  a.stable_history = x->history_is_stable;
   return kv4_decode_run(a, ST(stream));
 }
 

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <float.h>
+#include <mutex>
 
 namespace ob {
 
@@ -122,6 +123,11 @@ struct AttnParams {
   int sub_chunk, eles_per_ind;                          // LServe page statistics (sparse op): 0 = none
   // fused per-token INT8 quantisation of the attention output (extension): the last CTA of a sequence to finish
   int8_t* q_out; __half* q_scale; __half* q_sum; int* tok_counters;   // quantises the [Hq*128] row; null = off
+  // 1 = the caller guarantees that lengths, head tables, page tables, the dynamic page list and every page except the
+  // newest were last written BEFORE the kernel that precedes this launch in the stream (the decode loop: the qkv GEMM
+  // precedes, pages older than the newest are >= 1 step old), so they may be read while that kernel is still draining.
+  // 0 (default of the drop-in ops) = nothing is read before the grid dependency has resolved.
+  int stable_history;
 };
 
 // invoke_quant(_fuse_sum) (fused_kernels.cu:57-142) of one attention-output row by the first 128 threads of the CTA,
@@ -287,6 +293,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
   __shared__ float red_s[64];
 
   pdl_trigger();
+  if (!p.stable_history) pdl_wait();   // e.g. a decode launched straight after the prefill writer of the same pages
   const int split = blockIdx.x;
   const int b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -789,26 +796,48 @@ __global__ void padding_offsets_kernel(int* out, const int* cu, int max_seq_len)
 }
 
 // ---------------------------------------------------------------------------------------------- host
-static float* g_part_o[16] = {nullptr};
-static float* g_part_ml[16] = {nullptr};
-static int* g_att_cnt[16] = {nullptr};
-static size_t g_part_cap[16] = {0};
-static int g_att_sms = 0;
+// Split-KV scratch: one fixed-size workspace per (device, stream), carved out of a pool that is allocated once on the
+// first call on a device and never freed or moved -- pointers baked into captured CUDA graphs stay valid, and two
+// streams running attention concurrently never share partials or arrival counters.
+constexpr int ATT_MAX_DEV = 16;
+constexpr int ATT_MAX_STREAMS = 8;
+constexpr size_t ATT_MAX_SLOTS = 4096;          // (sequence, head group, split) partials; 4 KB + 64 B each
+constexpr size_t ATT_CNT_INTS = 65536 + 32768;  // [0, 65536): split arrival counters; [65536, ...): fused-quant counters
+struct AttWs { cudaStream_t st; float* part_o; float* part_ml; int* cnt; };
+struct AttDev { int sms = 0; AttWs ws[ATT_MAX_STREAMS] = {}; int n = 0; };
+static AttDev g_att[ATT_MAX_DEV];
+static std::mutex g_att_mu;
 
-static int ensure_att_ws(int dev, size_t slots, int G) {
-  const size_t need = slots * G;
-  if (g_part_cap[dev] >= need && g_att_cnt[dev]) return 0;
-  if (g_part_o[dev]) { cudaFree(g_part_o[dev]); cudaFree(g_part_ml[dev]); }
-  if (cudaMalloc(&g_part_o[dev], need * DH * 4) != cudaSuccess) return OB_ERR_CUDA;
-  if (cudaMalloc(&g_part_ml[dev], need * 2 * 4) != cudaSuccess) return OB_ERR_CUDA;
-  g_part_cap[dev] = need;
-  if (!g_att_cnt[dev]) {
-    // [0, 65536): split-KV arrival counters per (sequence, head group); [65536, 98304): per-sequence counters of the
-    // fused output quantisation
-    if (cudaMalloc(&g_att_cnt[dev], (65536 + 32768) * 4) != cudaSuccess) return OB_ERR_CUDA;
-    cudaMemset(g_att_cnt[dev], 0, (65536 + 32768) * 4);
+static int att_sms(int dev) {
+  if (!g_att[dev].sms) cudaDeviceGetAttribute(&g_att[dev].sms, cudaDevAttrMultiProcessorCount, dev);
+  return g_att[dev].sms;
+}
+
+static int get_att_ws(int dev, cudaStream_t st, AttWs* out) {
+  std::lock_guard<std::mutex> lk(g_att_mu);
+  AttDev& d = g_att[dev];
+  if (!d.ws[0].part_o) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return OB_ERR_ARG;   // first use must be outside graph capture (warm-up)
+    const size_t o_f = ATT_MAX_SLOTS * 8 * DH, ml_f = ATT_MAX_SLOTS * 8 * 2;
+    float* po = nullptr; float* pm = nullptr; int* pc = nullptr;
+    if (cudaMalloc(&po, o_f * 4 * ATT_MAX_STREAMS) != cudaSuccess) return OB_ERR_CUDA;
+    if (cudaMalloc(&pm, ml_f * 4 * ATT_MAX_STREAMS) != cudaSuccess) return OB_ERR_CUDA;
+    if (cudaMalloc(&pc, ATT_CNT_INTS * 4 * ATT_MAX_STREAMS) != cudaSuccess) return OB_ERR_CUDA;
+    cudaMemset(pc, 0, ATT_CNT_INTS * 4 * ATT_MAX_STREAMS);
     cudaDeviceSynchronize();
+    for (int i = 0; i < ATT_MAX_STREAMS; ++i) {
+      d.ws[i].part_o = po + (size_t)i * o_f;
+      d.ws[i].part_ml = pm + (size_t)i * ml_f;
+      d.ws[i].cnt = pc + (size_t)i * ATT_CNT_INTS;
+    }
   }
+  for (int i = 0; i < d.n; ++i)
+    if (d.ws[i].st == st) { *out = d.ws[i]; return 0; }
+  if (d.n == ATT_MAX_STREAMS) return OB_ERR_ARG;
+  d.ws[d.n].st = st;
+  *out = d.ws[d.n++];
   return 0;
 }
 
@@ -822,7 +851,9 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
   if (G < 1 || G > 8) return OB_ERR_SHAPE;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!g_att_sms) cudaDeviceGetAttribute(&g_att_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev < 0 || dev >= ATT_MAX_DEV) return OB_ERR_ARG;
+  const int g_att_sms = att_sms(dev);
+  AttWs ws{};
 
   AttnParams p{};
   p.q = a.q; p.k = a.k; p.v = a.v; p.q_bs = a.q_bs; p.k_bs = a.k_bs; p.v_bs = a.v_bs; p.out = a.out;
@@ -838,10 +869,11 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
   p.timestep = a.timestep;
   p.sub_chunk = a.tokens_per_sub_chunk; p.eles_per_ind = a.hidden_dim_per_retrieval_token;
   p.q_out = a.q_out; p.q_scale = a.q_scale; p.q_sum = a.q_sum; p.tok_counters = nullptr;
+  p.stable_history = a.stable_history;
   if (p.q_out) {
     if (!p.q_scale || (a.Hq * DH) % 8 || (a.Hq * DH) / 8 > 8 * 128 || a.B > 32768) return OB_ERR_SHAPE;
-    if (int e = ensure_att_ws(dev, 1, 8)) return e;          // allocates the counter array (65536 ints) once
-    p.tok_counters = g_att_cnt[dev] + 65536;
+    if (int e = get_att_ws(dev, st, &ws)) return e;
+    p.tok_counters = ws.cnt + 65536;
   }
   if (p.sub_chunk < 0 || (p.sub_chunk > 0 && TPB % p.sub_chunk)) return OB_ERR_SHAPE;
 
@@ -856,9 +888,11 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
   if (a.force_split > 0) n_split = a.force_split;
   p.n_split = n_split;
   if (n_split > 1) {
-    if (base_ctas > 65536) return OB_ERR_SHAPE;
-    if (int e = ensure_att_ws(dev, (size_t)base_ctas * n_split, 8)) return e;
-    p.part_o = g_part_o[dev]; p.part_ml = g_part_ml[dev]; p.counters = g_att_cnt[dev];
+    // the workspace is fixed-size: automatic splits stay below ~2 * 4 * #SMs partials; a forced split that needs more
+    // is rejected rather than growing (and moving) the buffer
+    if (base_ctas > 65536 || (size_t)base_ctas * n_split > ATT_MAX_SLOTS) return OB_ERR_ARG;
+    if (!ws.part_o) { if (int e = get_att_ws(dev, st, &ws)) return e; }
+    p.part_o = ws.part_o; p.part_ml = ws.part_ml; p.counters = ws.cnt;
   }
   dim3 grid(n_split, ctas_y, a.B);
   return launch_pdl(kv4_decode_kernel, grid, dim3(V2_THREADS), (size_t)(V2_STAGES * V2_STAGE_BYTES), st, p, G) == cudaSuccess

@@ -28,6 +28,7 @@ struct KV4DecodeArgs {
   int8_t* q_out = nullptr; __half* q_scale = nullptr; __half* q_sum = nullptr;   // fused output quant (extension)
   int tokens_per_sub_chunk = 0;                        // > 0: fold the appended key into the page's kmax / kmin
   int hidden_dim_per_retrieval_token = 0;
+  int stable_history = 0;                              // see AttnParams::stable_history
 };
 
 int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st);

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(256) page_selector_kernel(const SelParams p) {
   __shared__ __align__(16) __half q_s[G][LS_DH];
   __shared__ float rope_cs[LS_DH / 2], rope_sn[LS_DH / 2];
   pdl_trigger();
+  pdl_wait();   // lengths / q (and, in principle, the tables) may be the previous kernel's output: read nothing before
   const int b = blockIdx.z, hkv = blockIdx.y;
   if (p.retrieval_flags && p.retrieval_flags[hkv] == 0) return;   // streaming heads keep their zero rows
   const int rank = p.head_rank ? p.head_rank[hkv] : hkv;
@@ -171,7 +172,6 @@ __global__ void __launch_bounds__(256) page_selector_kernel(const SelParams p) {
     const float inv_freq = ((float)tl * p.rope_scale) / powf(p.rope_base, (float)(2 * tid) / (float)p.rotary_dim);
     sincosf(inv_freq, &rope_sn[tid], &rope_cs[tid]);
   }
-  pdl_wait();
   __syncthreads();
   const int hq0 = hkv * G;
   for (int item = tid; item < G * (LS_DH / 2); item += 256) {

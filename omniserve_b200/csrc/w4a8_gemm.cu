@@ -193,6 +193,14 @@ OB_DEVICE void tile_coords(const GemmParams& p, int tile, int& nt, int& mt) {
 // Timing experiments (compile with -DOB_GEMM_TIMING, run tools/gemm_waits.py): accumulate the cycles a role spends in a
 // wait into tw[slot] and dump them to p.dbg_t.  Compiled out by default: even disabled at run time the extra branches and
 // accumulators cost ~20 % of the kernel's throughput (measured, round 1).
+// Timing / ablation experiments (tools/gemm_micro.py): `-DOB_GEMM_DEBUG` compiles the OB_GEMM_DBG bit tests into the
+// role loops; the shipped build has none of these branches.
+#ifdef OB_GEMM_DEBUG
+#define OB_DBG(mask) ((p.dbg & (mask)) != 0)
+#else
+#define OB_DBG(mask) false
+#endif
+
 #ifdef OB_GEMM_TIMING
 #define OB_TW(slot, call)                  \
   do {                                     \
@@ -270,7 +278,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
   __syncthreads();
   tc_fence_after();
   // all CTAs of the cluster run (barriers initialised) before any DSMEM store / multicast copy / remote arrive targets them
-  if ((p.mode == 2 && !(p.dbg & 16)) || p.mc > 1) cluster_barrier();
+  if ((p.mode == 2 && !OB_DBG(16)) || p.mc > 1) cluster_barrier();
   const uint32_t tmem_base = *tmem_slot;
 
 
@@ -290,8 +298,8 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       while (it.next(p)) {
         OB_TW(0, mbar_wait(&w_empty[stage], phase ^ 1));
         const int n_cnt = min(BM, p.N - it.nt * BM);
-        mbar_arrive_expect_tx(&w_full[stage], ((p.dbg & 64) ? 0 : W_STAGE) + (PER_GROUP ? 2 * n_cnt : 0));
-        if (!(p.dbg & 64)) {
+        mbar_arrive_expect_tx(&w_full[stage], (OB_DBG(64) ? 0 : W_STAGE) + (PER_GROUP ? 2 * n_cnt : 0));
+        if (!OB_DBG(64)) {
           if (p.w_rows2k) tma_load_3d(sW + stage * W_STAGE, &w_map, 0, it.kb, it.nt * 4, &w_full[stage]);
           else tma_load_3d(sW + stage * W_STAGE, &w_map, 0, it.kb * 4, it.nt * 4, &w_full[stage]);
         }
@@ -338,8 +346,8 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
       } else {
         while (it.next(p)) {
           OB_TW(0, mbar_wait(&ba_empty[stage], phase ^ 1));
-          mbar_arrive_expect_tx(&b_full[stage], (p.dbg & 32) ? 0 : C::B_STAGE);
-          if (!(p.dbg & 32)) tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, it.mt * BN, &b_full[stage]);
+          mbar_arrive_expect_tx(&b_full[stage], OB_DBG(32) ? 0 : C::B_STAGE);
+          if (!OB_DBG(32)) tma_load_2d(sB + stage * C::B_STAGE, &act_map, it.kb * BK, it.mt * BN, &b_full[stage]);
           if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -413,7 +421,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
         if (elect_one()) {
           const uint64_t bdesc = bdesc0 + (uint64_t)((st * C::B_STAGE) >> 4);
           const uint32_t a_tmem = a_tmem0 + st * A_COLS_PER_STAGE;
-          if (!(p.dbg & 4)) {
+          if (!OB_DBG(4)) {
             umma_i8_ts(d_tmem, a_tmem, bdesc, idesc, kb > sg.kb0 ? 1u : 0u);
             umma_i8_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc, 1u);
             umma_i8_ts(d_tmem, a_tmem + 16, bdesc + 4, idesc, 1u);
@@ -483,7 +491,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     };
     auto flush_pending = [&]() {
       if (pend0 >= 0) {   // previous K-block(s): their TMEM stores have had a whole iteration to land
-        if (!(p.dbg & 1)) tmem_st_wait();
+        if (!OB_DBG(1)) tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -497,7 +505,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
     while (it.next(sg)) {
       for (int kb = sg.kb0; kb < sg.kb1;) {
         OB_TW(0, mbar_wait(&w_full[ws], wph));
-        if (p.dbg & 2) {
+        if (OB_DBG(2)) {
           __syncwarp();
           if (lane == 0) { mbar_arrive(&w_empty[ws]); }
           mbar_wait(&ba_empty[as], aph ^ 1);
@@ -614,7 +622,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_const
             const int owner = col / cp;
             const int lc = col - owner * cp;
             const uint32_t off = (uint32_t)(((my * cp + lc) * BM + q * 32 + lane) * 4);
-            if (owner == my || (p.dbg & 8)) stage32[(my * cp + lc) * BM + q * 32 + lane] = (int)r[j];
+            if (owner == my || OB_DBG(8)) stage32[(my * cp + lc) * BM + q * 32 + lane] = (int)r[j];
             else st_shared_cluster_u32(mapa_shared(base_local + off, (uint32_t)owner), r[j]);
           }
         }
@@ -863,20 +871,78 @@ static int make_w_map(CUtensorMap* out, const void* ptr, int N, int K, bool rows
   return 0;
 }
 
-static int g_num_sms = 0;
-static int32_t* g_ws[16] = {nullptr};
-static int32_t* g_cnt[16] = {nullptr};
+// Per-device state (one process may drive several GPUs) and one split-K workspace per (device, stream): two streams
+// running GEMMs concurrently must not share partial sums or arrival counters.  Workspaces are allocated once at their
+// bounded maximum and never freed or moved, so pointers baked into captured CUDA graphs stay valid.
+constexpr int MAX_DEV = 16;
+constexpr int MAX_STREAMS_PER_DEV = 8;
 constexpr size_t WS_INTS_PER_CTA = 128 * 128;  // BN(max 128 in SK mode) * BM
+struct GemmWs { cudaStream_t st; int32_t* ws; int32_t* cnt; bool used; };
+struct DevState {
+  int sms = 0;
+  GemmWs ws[MAX_STREAMS_PER_DEV] = {};
+  int n_ws = 0;
+};
+static DevState g_dev[MAX_DEV];
+static std::mutex g_dev_mu;
 
-static int ensure_workspace(int dev, int sms) {
-  if (g_ws[dev]) return 0;
-  size_t bytes = (size_t)sms * WS_INTS_PER_CTA * 4;
-  if (cudaMalloc(&g_ws[dev], bytes) != cudaSuccess) return OB_ERR_CUDA;
-  if (cudaMalloc(&g_cnt[dev], (sms + 2) * 4) != cudaSuccess) return OB_ERR_CUDA;   // + grid-barrier counter / generation
-  cudaMemset(g_ws[dev], 0, bytes);
-  cudaMemset(g_cnt[dev], 0, (sms + 2) * 4);
-  cudaDeviceSynchronize();
+static int dev_sms(int dev) {
+  if (!g_dev[dev].sms) cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev);
+  return g_dev[dev].sms;
+}
+
+static int get_workspace(int dev, cudaStream_t st, int32_t** ws, int32_t** cnt) {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DevState& d = g_dev[dev];
+  if (!d.ws[0].ws) {
+    // the whole pool is allocated on the first launch on this device (which must be outside graph capture: cudaMalloc is
+    // not capturable); later streams only get a slot ASSIGNED, which is legal during capture
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return OB_ERR_ARG;
+    const int sms = dev_sms(dev);
+    const size_t bytes = (size_t)sms * WS_INTS_PER_CTA * 4, cbytes = (size_t)(sms + 2) * 4;
+    int32_t* all = nullptr;
+    int32_t* call = nullptr;
+    if (cudaMalloc(&all, bytes * MAX_STREAMS_PER_DEV) != cudaSuccess) return OB_ERR_CUDA;
+    if (cudaMalloc(&call, cbytes * MAX_STREAMS_PER_DEV) != cudaSuccess) return OB_ERR_CUDA;
+    cudaMemset(all, 0, bytes * MAX_STREAMS_PER_DEV);
+    cudaMemset(call, 0, cbytes * MAX_STREAMS_PER_DEV);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < MAX_STREAMS_PER_DEV; ++i) {
+      d.ws[i].ws = all + (size_t)i * (bytes / 4);
+      d.ws[i].cnt = call + (size_t)i * (sms + 2);
+      d.ws[i].used = false;
+    }
+  }
+  for (int i = 0; i < d.n_ws; ++i)
+    if (d.ws[i].st == st) { *ws = d.ws[i].ws; *cnt = d.ws[i].cnt; return 0; }
+  if (d.n_ws == MAX_STREAMS_PER_DEV) return OB_ERR_ARG;   // more distinct GEMM streams than workspaces
+  GemmWs& w = d.ws[d.n_ws++];
+  w.st = st; w.used = true;
+  *ws = w.ws; *cnt = w.cnt;
   return 0;
+}
+
+// Experiment switches are read from the environment ONCE (first launch); OB_GEMM_ENV_RELOAD=1 (tools/gemm_micro.py)
+// re-reads them on every launch.
+struct GemmEnv { int dbg, unpack2, mc, two, w2k; long long* dbg_t; bool has_two; };
+static GemmEnv read_env() {
+  GemmEnv e{};
+  const char* v;
+  v = getenv("OB_GEMM_DBG"); e.dbg = v ? atoi(v) : 0;
+  v = getenv("OB_GEMM_UNPACK2"); e.unpack2 = v ? atoi(v) : 1;
+  v = getenv("OB_GEMM_DBGT"); e.dbg_t = v ? reinterpret_cast<long long*>(strtoull(v, nullptr, 10)) : nullptr;
+  v = getenv("OB_GEMM_MC"); e.mc = v ? atoi(v) : 1;
+  v = getenv("OB_GEMM_2CTA"); e.has_two = v != nullptr; e.two = v ? atoi(v) : 0;
+  v = getenv("OB_GEMM_W2K"); e.w2k = (v && atoi(v)) ? 1 : 0;
+  return e;
+}
+static const GemmEnv& gemm_env() {
+  static const bool reload = getenv("OB_GEMM_ENV_RELOAD") != nullptr;
+  static GemmEnv e = read_env();
+  if (reload) e = read_env();
+  return e;
 }
 
 template <int BN, bool PG, bool TWO = false>
@@ -884,15 +950,18 @@ static int launch(const CUtensorMap& map, const CUtensorMap& wmap, const CUtenso
                   unsigned cluster, cudaStream_t st) {
   using C = Cfg<BN, TWO>;
   auto kern = w4a8_gemm_kernel<BN, PG, TWO>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[MAX_DEV] = {};   // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL) != cudaSuccess)
       return OB_ERR_CUDA;
-    attr_done = true;
+    attr_done[dev] = true;
   }
   if (p.mc > 1) {
     // persistent multicast clusters: as many as can be co-resident (GPC sizes limit how many clusters of mc fit)
-    static int max_clusters[9] = {0};
+    static int max_clusters_dev[MAX_DEV][9] = {};
+    int* max_clusters = max_clusters_dev[dev];
     if (!max_clusters[p.mc]) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(p.mc * 64);
@@ -920,19 +989,21 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     return OB_ERR_ALIGN;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!g_num_sms) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev < 0 || dev >= MAX_DEV) return OB_ERR_ARG;
+  const int g_num_sms = dev_sms(dev);
   const int sms = (a.force_ctas > 0 && a.force_mode != 2) ? std::min(a.force_ctas, g_num_sms) : g_num_sms;
-  if (int e = ensure_workspace(dev, g_num_sms)) return e;
+  int32_t* ws_ptr = nullptr;
+  int32_t* cnt_ptr = nullptr;
+  if (int e = get_workspace(dev, st, &ws_ptr, &cnt_ptr)) return e;
+  const GemmEnv& env = gemm_env();
 
   int BN = a.M <= 16 ? 16 : a.M <= 32 ? 32 : a.M <= 64 ? 64 : 128;
   if (a.force_bn > 0) BN = a.force_bn;
   GemmParams p{};
-  { const char* e = getenv("OB_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
-  { const char* e = getenv("OB_GEMM_UNPACK2"); p.unpack2 = e ? atoi(e) : 1; }
-  { const char* e = getenv("OB_GEMM_DBGT"); p.dbg_t = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr; }
+  p.dbg = env.dbg; p.unpack2 = env.unpack2; p.dbg_t = env.dbg_t;
   p.qweight = a.qweight; p.s2_scales = a.s2_scales; p.s2_zeros = a.s2_zeros;
   p.wscales = a.wscales; p.ascales = a.ascales; p.w_szs = a.w_szs; p.a_ssums = a.a_ssums;
-  p.out = a.out_feats; p.ws = g_ws[dev]; p.counters = g_cnt[dev];
+  p.out = a.out_feats; p.ws = ws_ptr; p.counters = cnt_ptr;
   if (a.tail_hidden_in) {
     // fused add + norm + quant tail: decode-sized M, rows of <= 4096 halves (4 vectors per tail thread), N == row length
     if (a.M > 256 || a.N > TAIL_NV * TAIL_THREADS * 8 || (a.N & 7) || !a.tail_hidden_out || !a.tail_gamma || !a.tail_q ||
@@ -941,7 +1012,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     p.tail = 1;
     p.t_hidden_in = a.tail_hidden_in; p.t_hidden_out = a.tail_hidden_out; p.t_gamma = a.tail_gamma;
     p.t_q = a.tail_q; p.t_scale = a.tail_scale; p.t_sum = a.tail_sum; p.t_eps = a.tail_eps;
-    p.t_counter = reinterpret_cast<unsigned int*>(g_cnt[dev] + g_num_sms);
+    p.t_counter = reinterpret_cast<unsigned int*>(cnt_ptr + g_num_sms);
     p.t_gen = p.t_counter + 1;
   }
   p.M = a.M; p.N = a.N; p.K = a.K; p.ldc = a.ldc;
@@ -994,13 +1065,12 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     // mc = 4; profiles/r1_summary.md): L2 read traffic is not the limiter (the shared-memory port is: TMA writes +
     // packed-weight reads + UMMA B-operand reads ~ 48 KB per K-block), and lock-stepping the cluster costs more than
     // the saved L2 reads.  Opt-in for experiments: OB_GEMM_MC = 2 / 4.
-    int mc = 1;
-    { const char* e3 = getenv("OB_GEMM_MC"); if (e3) mc = atoi(e3); }
+    int mc = env.mc;
     if (mc < 1 || mc > 4 || (mc & (mc - 1)) || p.n_tiles % mc || BN % (8 * mc) || a.force_ctas > 0) mc = 1;
     // CTA-pair MMA (tcgen05 cta_group::2): 256 weight rows x 128 tokens per pair, each CTA stages half of the tokens.
     // OB_GEMM_2CTA = 0 / 1 overrides the automatic choice (large-M data-parallel problems).
     two = 0;  // opt-in until it beats the single-CTA kernel (profiles/r1_summary.md)
-    { const char* e4 = getenv("OB_GEMM_2CTA"); if (e4) two = (atoi(e4) != 0 && BN == 128 && p.n_tiles % 2 == 0 && a.force_ctas <= 0) ? 1 : 0; }
+    if (env.has_two) two = (env.two != 0 && BN == 128 && p.n_tiles % 2 == 0 && a.force_ctas <= 0) ? 1 : 0;
     if (p.tail) { two = 0; mc = 1; }   // the fused tail is only wired into the plain single-CTA schedule
     if (two) mc = 2;
     p.mc = mc;
@@ -1014,7 +1084,7 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
     if (int e = make_act_map(&mcmap, a.in_feats, a.M, a.K, BN / p.mc)) return e;
   }
   CUtensorMap wmap;
-  { const char* e2 = getenv("OB_GEMM_W2K"); p.w_rows2k = (e2 && atoi(e2)) ? 1 : 0; }
+  p.w_rows2k = env.w2k;
   if (int e = make_w_map(&wmap, a.qweight, a.N, a.K, p.w_rows2k != 0)) return e;
 #define OB_LAUNCH(bn)                                                              \
   case bn:                                                                         \

@@ -345,7 +345,7 @@ class LlamaW4A8:
                     q3, k3, v3, self.kv.tables[li], meta["context_lens"], None, self.max_ctx, TOKENS_PER_BLOCK,
                     self.kv_size // 2, meta["timestep"], cfg.head_dim, cfg.rope_theta, True, True, True,
                     b.quantized_attn_buffer[:T], b.quantized_sum_buffer[:T] if self.act_sum else None,
-                    b.quantized_scale_buffer[:T]).reshape(T, self.q_size)
+                    b.quantized_scale_buffer[:T], history_is_stable=True).reshape(T, self.q_size)
             else:
                 attn = fused_attention_pure_dense.single_query_attention(
                     q3, k3, v3, self.kv.tables[li], meta["context_lens"], None, self.max_ctx, TOKENS_PER_BLOCK,
@@ -441,6 +441,9 @@ class LlamaW4A8:
         T = tokens.numel()
         B = len(seq_lens)
         dev = self.device
+        assert self.buf is not None and T <= self.buf.T, f"prefill of {T} tokens exceeds the activation arena ({self.buf.T})"
+        assert T == sum(seq_lens) and seq_offset + B <= self.batch
+        assert max(seq_lens) <= self.kv.pages_per_seq * TOKENS_PER_BLOCK, "prompt longer than the per-sequence page budget"
         sl = torch.tensor(seq_lens, dtype=torch.int32, device=dev)
         cu = torch.zeros(B + 1, dtype=torch.int32, device=dev)
         cu[1:] = torch.cumsum(sl, 0)
@@ -472,6 +475,9 @@ class LlamaW4A8:
         the cached context over the batch (host int, baked into launch configs / CUDA graphs).  context_lens
         (device) is advanced by one inside the step."""
         B = tokens.numel()
+        # `timestep` bounds the cached context of every sequence; the token appended by this step lands at position
+        # <= timestep, which must exist in the page tables (the kernels trust the pointers)
+        assert B <= self.buf.T and timestep < self.kv.pages_per_seq * TOKENS_PER_BLOCK + 1 and timestep <= self.max_ctx
         self.context_lens.add_(1)  # length incl. the new token (decoding_attention.py:151-153)
         meta = {"context_lens": self.context_lens, "timestep": timestep}
         if not self.fuse_silu_quant:
@@ -496,6 +502,8 @@ class DecodeGraph:
         self.out = torch.zeros((B,), dtype=torch.int64, device=model.device)
         model.prepare_decode()
         saved = model.context_lens.clone()
+        # the warm-up steps append `warmup` tokens per sequence before the lengths are restored
+        assert int(saved.max()) + warmup <= model.kv.pages_per_seq * TOKENS_PER_BLOCK, "no page room for the warm-up steps"
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

@@ -154,6 +154,12 @@ def main() -> int:
             print(f"[build_ref] LINK FAILED {m}\n{r.stderr[-3000:]}", file=sys.stderr)
         else:
             print(f"[build_ref] linked {so}")
+    # launch interposer for the reference selector's missing dynamic shared memory (see oracle/ref_launch_shim.c)
+    shim_src = os.path.join(HERE, "ref_launch_shim.c")
+    shim = os.path.join(OUT, "libref_launch_shim.so")
+    if os.path.exists(shim_src) and (not os.path.exists(shim) or os.path.getmtime(shim) < os.path.getmtime(shim_src)):
+        r = subprocess.run(["gcc", "-shared", "-fPIC", "-O2", "-o", shim, shim_src, "-ldl"], capture_output=True, text=True)
+        print(f"[build_ref] {'built' if r.returncode == 0 else 'FAILED'} {shim} {r.stderr[-500:]}")
     print(f"[build_ref] done: {len(mods) - len(failed)}/{len(mods)} modules; failed={sorted(failed)}")
     return 1 if failed else 0
 

@@ -6,10 +6,23 @@ import numpy as np
 import pytest
 import torch
 
-from tests.gpu_util import qkv_views, t
+from tests.gpu_util import qkv_views, ref_module, t
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-3
+NORTH_STAR = 1e-3
+
+
+def _vs_reference_kernel(tag, got, exact, ref_out):
+    """Row a8 pinning: the same case through the REFERENCE's rebuilt kernel (oracle/_ref).  Our distance to exact
+    arithmetic must not exceed the reference's own (or the 1e-3 north-star tolerance, whichever is larger), and the two
+    kernels must agree to 3e-3 of the output scale."""
+    sc = np.abs(exact).max()
+    e_ours, e_ref = np.abs(got - exact).max() / sc, np.abs(ref_out - exact).max() / sc
+    d = np.abs(got - ref_out).max() / sc
+    print(f"\n{tag}: |ours-exact|={e_ours:.3e} |ref-exact|={e_ref:.3e} |ours-ref|={d:.3e}")
+    assert e_ours <= max(e_ref, NORTH_STAR)
+    assert d <= 3e-3
 
 
 def _ring(blk, sink_blk, local_blk):
@@ -70,11 +83,23 @@ def test_streaming_heads_sink_plus_local_ring(lens):
         n_valid = min(sink + local - 1, tl)
         gap = tl - n_valid
         return np.array([i if i < sink else i + gap for i in range(n_valid)], dtype=np.int64)
+    pools0 = (cache.k_pool.copy(), cache.v_pool.copy())
     ref = kv4.decode_attention(q, k, v, cache, virt, lens, 128, 500000.0, mimic=False, positions_fn=positions).astype(np.float32)
     got = out.cpu().numpy().astype(np.float32)
     assert np.abs(got - ref).max() <= TOL * np.abs(ref).max()
     np.testing.assert_array_equal(kpool.cpu().numpy(), cache.k_pool)   # append went through the ring mapping
     np.testing.assert_array_equal(vpool.cpu().numpy(), cache.v_pool)
+    rm = ref_module("fused_attention_fine_grained_dense")
+    if rm is not None:
+        cache.k_pool[:], cache.v_pool[:] = pools0
+        kpool2, vpool2, ptrs2 = _ptrs(cache, tables)
+        o2 = rm.single_query_attention(tq, tk, tv, None, ptrs2, flags, rank, t(np.asarray(lens, np.int32)), None, 2048, 64,
+                                       0, Hkv * Dh // 2, sink, local, sink_blk, local_blk, 0, Hkv, max(lens) - 1, 128,
+                                       500000.0, 1.0, True, True, True, 2048)
+        torch.cuda.synchronize()
+        _vs_reference_kernel(f"streaming heads lens={lens}", got, ref, o2.float().cpu().numpy())
+        assert (vpool2 != vpool).float().mean() == 0     # V bytes identical; K differs only through RoPE intrinsics
+        assert (kpool2 != kpool).float().mean() < 1e-3
 
 
 @pytest.mark.parametrize("lens,P", [((700, 300), 4), ((1281, 1025), 9), ((64, 65), 1)])
@@ -116,12 +141,24 @@ def test_dynamic_page_selection(lens, P):
             n = 64 if j < P - 1 else (tl - 1) % 64 + 1
             pos.extend(range(int(dyn[b, hq, j]) * 64, int(dyn[b, hq, j]) * 64 + n))
         return np.asarray(pos, np.int64)
+    pools0 = (cache.k_pool.copy(), cache.v_pool.copy())
     ref = kv4.decode_attention(q, k, v, cache, bt, lens, 128, 500000.0, mimic=False, positions_fn=positions,
                                update_stats_sub_chunk=16).astype(np.float32)
     got = out.cpu().numpy().astype(np.float32)
     assert np.abs(got - ref).max() <= TOL * np.abs(ref).max()
     assert_k_pool_equal(kpool, cache)   # nibbles, scales, zeros exact; kmax / kmin to the last fp16 bits
     np.testing.assert_array_equal(vpool.cpu().numpy(), cache.v_pool)
+    rm = ref_module("fused_attention_fine_grained_sparse")
+    if rm is not None:
+        cache.k_pool[:], cache.v_pool[:] = pools0
+        kpool2, vpool2, ptrs2 = device_tables(cache, bt)
+        o2 = rm.single_query_attention(tq, tk, tv, ptrs2, None, flags, rank, t(dyn), t(np.asarray(lens, np.int32)), None, 4096,
+                                       64, Hkv * 64, 0, 0, 0, 0, 0, Hkv, 0, max(lens) - 1, 128, 500000.0, 1.0, True, True,
+                                       True, 16, Hkv * 128, 2048)
+        torch.cuda.synchronize()
+        _vs_reference_kernel(f"dynamic pages lens={lens} P={P}", got, ref, o2.float().cpu().numpy())
+        assert (vpool2 != vpool).float().mean() == 0
+        assert (kpool2 != kpool).float().mean() < 2e-3   # incl. the kmax / kmin fold of the appended (fast-math RoPE) key
 
 
 def test_mixed_retrieval_and_streaming_heads_with_rank_table():
@@ -170,3 +207,108 @@ def test_mixed_retrieval_and_streaming_heads_with_rank_table():
         assert np.abs(mine - ref).max() <= TOL * np.abs(ref).max()
     np.testing.assert_array_equal(rk.cpu().numpy(), rc.k_pool)
     np.testing.assert_array_equal(sk.cpu().numpy(), sc.k_pool)
+
+
+def _random_pages(cache, rng):
+    """Valid random KV4 pages without running the per-token quantiser: any nibble bytes, positive scales, mid-range
+    zero points, N(0,1) statistics.  (The attention reads whatever the pages hold.)"""
+    for pool in (cache.k_pool, cache.v_pool):
+        pool[:, :cache.data_bytes] = rng.integers(0, 256, (cache.P, cache.data_bytes), dtype=np.uint8)
+        n = cache.sz_bytes // 4
+        sz = pool[:, cache.data_bytes:cache.data_bytes + cache.sz_bytes].view(np.float16)
+        sz[:, :n] = rng.uniform(0.05, 0.15, (cache.P, n)).astype(np.float16)
+        sz[:, n:] = rng.uniform(6.0, 9.0, (cache.P, n)).astype(np.float16)
+    if cache.stats_bytes:
+        st = cache.k_pool[:, cache.data_bytes + cache.sz_bytes:].view(np.float16)
+        st[:] = rng.standard_normal(st.shape).astype(np.float16)
+
+
+def test_c3_shape_256k_context_head_split_from_fixture():
+    """BASELINE config 3 shape: Llama-3-8B-Instruct-Gradient-1048k, bs = 1, 262 144 cached tokens, dynamic budget 4096
+    tokens -> P = 64 pages per retrieval q-head, streaming heads attend 128 sink + 256 local tokens through the ring,
+    retrieval / streaming head split of one layer from the reference's attn_patterns TSV at static_sparsity 0.5
+    (tests/golden/head_split_llama3_8b_1048k_s50.json, derived by tests/golden/make_head_split.py with the rule of
+    omniserve/attn_config.py:113-150).  Checked against the exact oracle and the reference's sparse kernel."""
+    import json
+    import os
+    from omniserve_b200.backend import fused_attention_fine_grained_sparse as op
+    from oracle import kv4
+    from tests.gpu_util import ROOT, device_tables
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "head_split_llama3_8b_1048k_s50.json")))
+    layer = 9
+    flags_np = np.asarray(fx["retrieval_head_flags"][layer], np.int32)
+    rank_np = np.asarray(fx["head_rank_table"][layer], np.int32)
+    Hq, Hkv, Dh, g = 32, 8, 128, 4
+    Hr, Hs = int(flags_np.sum()), int(Hkv - flags_np.sum())
+    assert 0 < Hr < Hkv
+    ctx, P = 262144, 64
+    lens = [ctx + 1]
+    sink, local, sink_blk, local_blk = 128, 256, 2, 5
+    rng = np.random.default_rng(2025)
+    n_pages = ctx // 64 + 1
+    rc = kv4.PagedKV4(n_pages, Hr, Dh, k_stats_subchunks=4)
+    _random_pages(rc, rng)
+    rbt = rng.permutation(n_pages).reshape(1, n_pages)
+    sc = kv4.PagedKV4(sink_blk + local_blk, Hs, Dh)
+    _random_pages(sc, rng)
+    stab = rng.permutation(sink_blk + local_blk).reshape(1, -1)
+    blks = np.arange(n_pages)
+    virt = stab[:, np.where(blks < sink_blk, blks, sink_blk + (blks - sink_blk) % local_blk)]
+    dyn = np.zeros((1, Hq, P), np.int32)
+    newest = (ctx - 1) // 64
+    for h in range(Hq):
+        dyn[0, h, :P - 1] = rng.choice(newest, P - 1, replace=False)
+        dyn[0, h, P - 1] = newest
+    q = rng.standard_normal((1, Hq, Dh)).astype(np.float16)
+    k = rng.standard_normal((1, Hkv, Dh)).astype(np.float16)
+    v = rng.standard_normal((1, Hkv, Dh)).astype(np.float16)
+    _, tq, tk, tv = qkv_views(q, k, v)
+    args = lambda rp, sp: (tq, tk, tv, rp, sp, t(flags_np), t(rank_np), t(dyn), t(np.asarray(lens, np.int32)), None,  # noqa: E731
+                           1 << 20, 64, Hr * 64, Hs * 64, sink, local, sink_blk, local_blk, Hr, Hs, ctx, 128, 500000.0, 1.0,
+                           True, True, True, 16, Hr * 128, 2048)
+    rk, rv, rptrs = device_tables(rc, rbt)
+    sk, sv_, sptrs = _ptrs(sc, stab)
+    out = op.single_query_attention(*args(rptrs, sptrs))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().astype(np.float32)
+    ref_out = None
+    rm = ref_module("fused_attention_fine_grained_sparse")
+    if rm is not None:
+        rk2, rv2, rptrs2 = device_tables(rc, rbt)
+        sk2, sv2, sptrs2 = _ptrs(sc, stab)
+        ref_out = rm.single_query_attention(*args(rptrs2, sptrs2)).float().cpu().numpy()
+        torch.cuda.synchronize()
+
+    def rpos(b, hq_local, tl):      # hq_local indexes the q heads of the retrieval pool in pool order
+        hq = r_q_heads[hq_local]
+        pos = []
+        for j in range(P):
+            n = 64 if j < P - 1 else (tl - 1) % 64 + 1
+            pos.extend(range(int(dyn[b, hq, j]) * 64, int(dyn[b, hq, j]) * 64 + n))
+        return np.asarray(pos, np.int64)
+
+    def spos(b, hq_local, tl):
+        n_valid = min(sink + local - 1, tl)
+        gap = tl - n_valid
+        return np.array([i if i < sink else i + gap for i in range(n_valid)], dtype=np.int64)
+    r_heads = [h for h in range(Hkv) if flags_np[h] == 1]
+    s_heads = [h for h in range(Hkv) if flags_np[h] == 0]
+    r_heads.sort(key=lambda h: rank_np[h])
+    s_heads.sort(key=lambda h: rank_np[h])
+    r_q_heads = [h * g + i for h in r_heads for i in range(g)]
+    exact = np.zeros_like(got)
+    for heads, cache, table, pf, kw in ((r_heads, rc, rbt, rpos, dict(update_stats_sub_chunk=16)), (s_heads, sc, virt, spos, {})):
+        qh = np.concatenate([q[:, h * g:(h + 1) * g] for h in heads], axis=1)
+        e = kv4.decode_attention(qh, k[:, heads], v[:, heads], cache, table, lens, 128, 500000.0, mimic=False,
+                                 positions_fn=pf, **kw).astype(np.float32)
+        for i, h in enumerate(heads):
+            exact[:, h * g:(h + 1) * g] = e[:, i * g:(i + 1) * g]
+    assert np.abs(got - exact).max() <= TOL * np.abs(exact).max()
+    # the appended token landed in page 4096 of the retrieval pool / through the ring in the streaming pool
+    from tests.gpu_util import assert_k_pool_equal
+    assert_k_pool_equal(rk, rc)
+    np.testing.assert_array_equal(rv.cpu().numpy(), rc.v_pool)
+    np.testing.assert_array_equal(sk.cpu().numpy(), sc.k_pool)
+    np.testing.assert_array_equal(sv_.cpu().numpy(), sc.v_pool)
+    if ref_out is not None:
+        _vs_reference_kernel("C3 shape (256K ctx, P=64, TSV head split)", got, exact, ref_out)
