@@ -103,11 +103,39 @@ def ref_loader():
     return load
 
 
-def cpu_baseline(cfg, seconds_budget: float = 20.0):
-    """torch-fp16 CPU path (oracle/cpu_path.py) for the same decode step on the host cores: ONE layer timed,
-    x32 extrapolated (bounded sample, stated in `sample`)."""
+def usable_cores() -> int:
+    """Host cores this process may really use: the scheduler affinity mask clipped by the cgroup CPU quota (the GPU lease
+    runs in a container; os.cpu_count() reports the whole host and oversubscribes a small quota 10-50x)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:   # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:   # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.5)))
+    return max(1, n)
+
+
+CPU_BASELINE_REPS = 5
+
+
+def cpu_baseline(cfg, reps: int = CPU_BASELINE_REPS):
+    """torch-fp16 CPU path (oracle/cpu_path.py) for the same decode step on the host cores: ONE layer timed a FIXED number
+    of times (min and median reported), x32 extrapolated (bounded sample, stated in `sample`)."""
     from oracle import cpu_path
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     c = dict(hidden=cfg.hidden_size, inter=cfg.intermediate_size, hq=cfg.num_attention_heads,
              hkv=cfg.num_key_value_heads, dh=cfg.head_dim, eps=cfg.rms_norm_eps, base=cfg.rope_theta)
@@ -119,16 +147,19 @@ def cpu_baseline(cfg, seconds_budget: float = 20.0):
     x = torch.randn(BATCH, c["hidden"], generator=g).half()
     lens = torch.full((BATCH,), ctx, dtype=torch.int64)
     cpu_path.decode_layer(x, p, kc, vc, lens, c)  # warm-up
-    best, n, t_all = 1e9, 0, time.perf_counter()
-    while n < 3 or (time.perf_counter() - t_all < seconds_budget and n < 20):
+    ts = []
+    for _ in range(reps):
         t0 = time.perf_counter()
         cpu_path.decode_layer(x, p, kc, vc, lens, c)
-        best = min(best, time.perf_counter() - t0)
-        n += 1
-    step_s = best * cfg.num_hidden_layers
-    return {"value": BATCH / step_s, "unit": "tok/s", "cores": cores, "kind": "port",
-            "sample": f"1 decoder layer (bs={BATCH}, ctx={ctx}) best of {n}, x{cfg.num_hidden_layers} layers "
-                      f"extrapolated; lm_head/embedding excluded; torch CPU fp16 storage / fp32 math"}
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    best, med = ts[0], ts[len(ts) // 2]
+    L = cfg.num_hidden_layers
+    return {"value": BATCH / (best * L), "value_median": BATCH / (med * L), "unit": "tok/s", "cores": cores, "kind": "port",
+            "host_cpu_count": os.cpu_count(), "layer_ms_min": best * 1e3, "layer_ms_median": med * 1e3,
+            "sample": f"1 decoder layer (bs={BATCH}, ctx={ctx}) x {reps} runs after 1 warm-up (value = fastest, value_median = "
+                      f"median), x{L} layers extrapolated; lm_head/embedding excluded; torch CPU fp16 storage / fp32 math; "
+                      f"threads = affinity mask clipped by the cgroup cpu quota"}
 
 
 def time_kernels(model, graph_ctx: int):

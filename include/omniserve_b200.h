@@ -42,8 +42,14 @@ int ob_w4a8_gemm_per_group(const int8_t* in_feats, const int8_t* kernel, const i
                            const int8_t* scales_i8, const void* wscales, const void* ascales, void* out_feats,
                            int M, int N, int K, int ldc, void* stream);
 
+/* ---- qgemm_w8a8.w8a8_gemm_forward_cuda (kernels/csrc/qgemm/w8a8/w8a8_gemm_cuda.cu:537-600, epilogue :515-530)
+ * out[M, ldc] (fp16) = (in[M,K] int8 . kernel[N,K]^T int8, s32 accumulate) * (wscales[n] * ascales[m]); kernel is plain
+ * row-major [N, K] (w8a8_linear.py:42-52).  N % 8 == 0, K % 128 == 0. */
+int ob_w8a8_gemm(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales, void* out_feats,
+                 int M, int N, int K, int ldc, void* stream);
+
 /* Same two GEMMs with scheduling knobs exposed for tests: force_bn in {0,16,32,64,128}, force_mode
- * -1 auto / 0 data-parallel tiles / 1 stream-K, force_ctas 0 = all SMs. */
+ * -1 auto / 0 data-parallel tiles / 1 stream-K / 2 cluster split-K / 3 decode kernel (M <= 64), force_ctas 0 = auto. */
 int ob_w4a8_gemm_ex(int per_group, const int8_t* in_feats, const int8_t* kernel, const int8_t* zeros,
                     const int8_t* scales_i8, const void* wscales, const void* ascales, const void* w_szs,
                     const void* a_ssums, void* out_feats, int M, int N, int K, int ldc, int force_bn,

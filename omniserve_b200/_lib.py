@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libomniserve_b200.so")
+LIB_PATH = os.environ.get("OB_LIB_PATH") or os.path.join(_HERE, "lib", "libomniserve_b200.so")   # override: instrumented builds
 
 _lib = None
 
@@ -76,6 +76,7 @@ _SIGS = {
     "ob_error_string": ([c_i], C.c_char_p),
     "ob_w4a8_gemm_per_chn": ([c_p] * 7 + [c_i] * 4 + [c_p], c_i),
     "ob_w4a8_gemm_per_group": ([c_p] * 7 + [c_i] * 4 + [c_p], c_i),
+    "ob_w8a8_gemm": ([c_p] * 5 + [c_i] * 4 + [c_p], c_i),
     "ob_w4a8_gemm_ex": ([c_i] + [c_p] * 9 + [c_i] * 7 + [c_p], c_i),
     "ob_w4a8_gemm_add_norm_quant": ([c_i] + [c_p] * 9 + [c_i] * 4 + [c_p] * 6 + [c_f] + [c_p], c_i),
     "ob_invoke_quant": ([c_p] * 3 + [c_i] * 2 + [c_p], c_i),

@@ -15,11 +15,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libomniserve_b200.so")
-SOURCES = ["w4a8_gemm.cu", "small_ops.cu", "kv4_attention.cu", "lserve_ops.cu", "c_api.cu"]
+SOURCES = ["w4a8_gemm.cu", "w4a8_gemm_decode.cu", "w8a8_gemm.cu", "small_ops.cu", "kv4_attention.cu", "lserve_ops.cu", "c_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--compiler-options", "-fPIC", "-Xptxas", "-v",
-] + (["-DOB_GEMM_TIMING"] if os.environ.get("OB_GEMM_TIMING") == "1" else [])  # per-role wait counters (tools/gemm_waits.py)
+] + (["-DOB_GEMM_TIMING"] if os.environ.get("OB_GEMM_TIMING") == "1" else []) + (
+    ["-DOB_DEC_TIMING"] if os.environ.get("OB_DEC_TIMING") == "1" else [])  # per-role wait counters (tools/gemm_waits.py)
 
 
 def _newest_src() -> float:

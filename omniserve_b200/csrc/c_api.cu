@@ -72,6 +72,12 @@ int ob_w4a8_gemm_per_group(const int8_t* in_feats, const int8_t* kernel, const i
                          ldc, 0, -1, 0, stream);
 }
 
+int ob_w8a8_gemm(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales, void* out_feats,
+                 int M, int N, int K, int ldc, void* stream) {
+  if (!in_feats || !kernel || !wscales || !ascales || !out_feats) return OB_ERR_ARG;
+  return w8a8_gemm_run(in_feats, kernel, H(wscales), H(ascales), HM(out_feats), M, N, K, ldc, ST(stream));
+}
+
 int ob_invoke_quant(int8_t* out, const void* input, void* scale, int T, int Hd, void* stream) {
   if (T <= 0) return 0;
   if (!out || !input || !scale) return OB_ERR_ARG;

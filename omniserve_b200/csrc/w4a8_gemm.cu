@@ -824,7 +824,7 @@ struct MapHash {
   }
 };
 
-static int make_act_map(CUtensorMap* out, const void* ptr, int M, int K, int BN) {
+int make_act_map(CUtensorMap* out, const void* ptr, int M, int K, int BN) {
   static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
@@ -846,7 +846,7 @@ static int make_act_map(CUtensorMap* out, const void* ptr, int M, int K, int BN)
   return 0;
 }
 
-static int make_w_map(CUtensorMap* out, const void* ptr, int N, int K, bool rows2k) {
+int make_w_map(CUtensorMap* out, const void* ptr, int N, int K, bool rows2k) {
   static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
@@ -886,12 +886,12 @@ struct DevState {
 static DevState g_dev[MAX_DEV];
 static std::mutex g_dev_mu;
 
-static int dev_sms(int dev) {
+int dev_sms(int dev) {
   if (!g_dev[dev].sms) cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev);
   return g_dev[dev].sms;
 }
 
-static int get_workspace(int dev, cudaStream_t st, int32_t** ws, int32_t** cnt) {
+int get_workspace(int dev, cudaStream_t st, int32_t** ws, int32_t** cnt) {
   std::lock_guard<std::mutex> lk(g_dev_mu);
   DevState& d = g_dev[dev];
   if (!d.ws[0].ws) {
@@ -901,7 +901,7 @@ static int get_workspace(int dev, cudaStream_t st, int32_t** ws, int32_t** cnt) 
     cudaStreamIsCapturing(st, &cs);
     if (cs != cudaStreamCaptureStatusNone) return OB_ERR_ARG;
     const int sms = dev_sms(dev);
-    const size_t bytes = (size_t)sms * WS_INTS_PER_CTA * 4, cbytes = (size_t)(sms + 2) * 4;
+    const size_t bytes = (size_t)sms * WS_INTS_PER_CTA * 4, cbytes = (size_t)GEMM_CNT_INTS(sms) * 4;
     int32_t* all = nullptr;
     int32_t* call = nullptr;
     if (cudaMalloc(&all, bytes * MAX_STREAMS_PER_DEV) != cudaSuccess) return OB_ERR_CUDA;
@@ -911,7 +911,7 @@ static int get_workspace(int dev, cudaStream_t st, int32_t** ws, int32_t** cnt) 
     cudaDeviceSynchronize();
     for (int i = 0; i < MAX_STREAMS_PER_DEV; ++i) {
       d.ws[i].ws = all + (size_t)i * (bytes / 4);
-      d.ws[i].cnt = call + (size_t)i * (sms + 2);
+      d.ws[i].cnt = call + (size_t)i * GEMM_CNT_INTS(sms);
       d.ws[i].used = false;
     }
   }
@@ -987,6 +987,15 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(a.in_feats) & 15) || (reinterpret_cast<uintptr_t>(a.out_feats) & 15) ||
       (reinterpret_cast<uintptr_t>(a.qweight) & 15))
     return OB_ERR_ALIGN;
+  // decode-sized problems go to the co-resident decode kernel (w4a8_gemm_decode.cu); force_mode 0 / 1 / 2 keep this
+  // file's schedules reachable (tests, A/B measurements), force_mode 3 insists on the decode kernel
+  {
+    static const bool v1_only = getenv("OB_GEMM_V1") != nullptr;
+    if (a.M <= 64 && !a.tail_hidden_in && (a.force_mode == 3 || (a.force_mode < 0 && !v1_only))) {
+      const int e = w4a8_gemm_decode_run(a, per_group, st);
+      if (e != OB_ERR_SHAPE || a.force_mode == 3) return e;
+    }
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= MAX_DEV) return OB_ERR_ARG;

@@ -1,4 +1,5 @@
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,5 +33,23 @@ struct W4A8GemmArgs {
 };
 
 int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st);
+
+// Decode-specialised kernel (w4a8_gemm_decode.cu): M <= 64, small enough (<= 113 KB shared memory, 256 tensor-memory
+// columns, <= 80 registers) for two CTAs per SM -- of the same GEMM, or of this GEMM and its PDL-launched successor.
+// force_ctas = grid override (0 = auto).  Returns OB_ERR_SHAPE for shapes it does not take (caller falls back).
+int w4a8_gemm_decode_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st);
+
+// W8A8 GEMM (w8a8_gemm.cu): out = (in . W^T) * wscales[n] * ascales[m], W plain row-major [N, K] int8.
+int w8a8_gemm_run(const int8_t* in_feats, const int8_t* weight, const __half* wscales, const __half* ascales, __half* out,
+                  int M, int N, int K, int ldc, cudaStream_t st);
+
+// ---- shared host-side helpers (w4a8_gemm.cu)
+int make_act_map(CUtensorMap* out, const void* ptr, int M, int K, int BN);          // [M, K] int8, box {128, BN}, SW128
+int make_w_map(CUtensorMap* out, const void* ptr, int N, int K, bool rows2k);       // packed W4 tiles, 8 KB per box
+int dev_sms(int dev);
+// split-K workspace of (device, stream): ws = [2 * #SMs][64 * 128] int32 (== [#SMs][128 * 128]), zero between launches;
+// cnt = GEMM_CNT_INTS(#SMs) int32 arrival counters, zero between launches
+#define GEMM_CNT_INTS(sms) (4 * (sms) + 8)
+int get_workspace(int dev, cudaStream_t st, int32_t** ws, int32_t** cnt);
 
 }  // namespace ob

@@ -1,0 +1,490 @@
+// W4A8 GEMM, decode-specialised (M <= 64) variant for sm_100a.  Same math, data path and operand formats as
+// w4a8_gemm.cu (packed INT4 -> INT8 in registers -> tensor-memory A operand -> tcgen05.mma kind::i8, INT32 accumulators
+// in TMEM, QServe dequant in the epilogue); what differs is everything that decides the LATENCY of a weight-streaming
+// launch (round-2 measurements, profiles/r2_stream_probe.log):
+//   * the bare load pipeline reaches the HBM roofline (6.6 TB/s) with four 8 KB stages per SM, yet the round-1 kernel
+//     took 0.26 us per K-block per CTA no matter how few CTAs ran: its four unpack warps each touch EVERY K-block
+//     (mbarrier wait -> ld.shared -> tcgen05.st -> wait::st -> arrive, ~500 cycles of dependent latency).  Here two
+//     sets of four unpack warps alternate K-blocks, so two K-blocks are in that chain at any time;
+//   * the CTA is small -- <= 99 KB shared memory, 256 tensor-memory columns, <= 80 registers x 384 threads -- so two
+//     CTAs fit on an SM: two CTAs of this GEMM (independent pipelines) or this GEMM's CTA next to the CTA of the next
+//     kernel of the decode chain, which programmatic dependent launch lets in early to prefetch ITS weights;
+//   * no shared-memory staging in the epilogue: split tiles are accumulated with red.global.add.s32 straight from the
+//     TMEM registers (128-byte coalesced, exact, order independent) and finished by the last contributor, full tiles are
+//     stored as fp16 directly; the unpack warps run the epilogue themselves (a decode CTA has 1-3 segments).
+//
+// Replaces the same reference kernels as w4a8_gemm.cu (per_chn/gemm_cuda.cu:308-657, per_group/gemm_cuda.cu:333-707).
+#include "launch.h"
+#include "ptx.cuh"
+#include "w4a8_gemm.h"
+
+#include <algorithm>
+#include <mutex>
+#include <stdlib.h>
+
+namespace ob {
+namespace dec {
+
+constexpr int BM = 128;                  // weight rows per tile (UMMA M, TMEM lanes)
+constexpr int BK = 128;                  // K bytes per stage
+constexpr int W_STAGE = BM * BK / 2;     // 8 KB packed
+constexpr int S2_STAGE = 256;            // per-group: 128 B scales + 128 B zeros
+constexpr int NUM_THREADS = 384;
+constexpr int A_COLS = BK / 4;           // 32 TMEM columns per unpacked K-block
+constexpr int TMEM_COLS = 256;
+constexpr int ACC_COLS = 64;
+constexpr int AB_STAGES = (TMEM_COLS - ACC_COLS) / A_COLS;   // 6: TMEM A ring and activation ring advance in lock-step
+
+template <int BN>
+struct Cfg {
+  static constexpr int W_STAGES = 6;
+  static constexpr int B_STAGE = BN * BK;
+  static constexpr int SMEM_B = 0;
+  static constexpr int SMEM_W = SMEM_B + AB_STAGES * B_STAGE;
+  static constexpr int SMEM_S2 = SMEM_W + W_STAGES * W_STAGE;
+  static constexpr int SMEM_TOK = SMEM_S2 + W_STAGES * S2_STAGE;   // float sa[BN], ss[BN]
+  static constexpr int SMEM_BAR = SMEM_TOK + BN * 8;
+  static constexpr int NUM_BARS = 2 * W_STAGES + 3 * AB_STAGES + 2;
+  static constexpr int SMEM_MISC = SMEM_BAR + NUM_BARS * 8;
+  static constexpr int SMEM_TOTAL = SMEM_MISC + 64 + 1024;        // + alignment slack
+  static_assert(SMEM_TOTAL <= 112 * 1024, "two CTAs per SM");
+};
+
+struct Params {
+  const int8_t* s2_scales; const int8_t* s2_zeros;
+  const __half* wscales; const __half* ascales; const __half* w_szs; const __half* a_ssums;
+  __half* out;
+  int32_t* ws;        // [grid][BN * 128] int32 partial tiles, zero between launches
+  int32_t* counters;  // [grid]
+  int M, N, K, ldc;
+  int n_tiles, kb_per_tile, units_per_cta;
+  long long* dbg_t;   // -DOB_DEC_TIMING builds only (tools/dec_waits.py): [grid][16] cycles per role
+};
+
+// Per-role cycle counters (compile with -DOB_DEC_TIMING, run tools/dec_waits.py); compiled out by default.
+#ifdef OB_DEC_TIMING
+#define OB_T(slot, call) do { const long long _t0 = clock64(); call; tw[slot] += clock64() - _t0; } while (0)
+#define OB_T_DECL(n) long long tw[n] = {}
+#define OB_T_DUMP(stmt) do { if (p.dbg_t) { stmt; } } while (0)
+#else
+#define OB_T(slot, call) call
+#define OB_T_DECL(n) (void)0
+#define OB_T_DUMP(stmt) (void)0
+#endif
+
+struct Seg { int tile, kb0, kb1; };
+
+// This CTA's contiguous range of (tile, K-block) units, cut into per-tile segments.
+struct SegIter {
+  int KB, pos, end;
+  OB_DEVICE void init(const Params& p) {
+    KB = p.kb_per_tile;
+    const long long tot = (long long)p.n_tiles * KB;
+    const long long b = (long long)blockIdx.x * p.units_per_cta, e = b + p.units_per_cta;
+    pos = (int)(b < tot ? b : tot);
+    end = (int)(e < tot ? e : tot);
+  }
+  OB_DEVICE bool next(Seg& s) {
+    if (pos >= end) return false;
+    s.tile = pos / KB;
+    s.kb0 = pos - s.tile * KB;
+    const int room = KB - s.kb0, left = end - pos;
+    s.kb1 = s.kb0 + (left < room ? left : room);
+    pos += s.kb1 - s.kb0;
+    return true;
+  }
+};
+
+OB_DEVICE uint32_t vadd4(uint32_t a, uint32_t b) {   // bytewise (a + b) mod 256, `__vadd4` of per_group/gemm_cuda.cu:307
+  const uint32_t s = (a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu);
+  return s ^ ((a ^ b) & 0x80808080u);
+}
+
+OB_DEVICE void red_add_s32(int32_t* addr, int32_t v) {
+  asm volatile("red.global.add.s32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+OB_DEVICE void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the eight unpack / epilogue warps
+
+template <int BN, bool PER_GROUP>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_constant__ CUtensorMap w_map, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem + C::SMEM_B;
+  uint8_t* sW = smem + C::SMEM_W;
+  uint8_t* sS2 = smem + C::SMEM_S2;
+  float* sTok = reinterpret_cast<float*>(smem + C::SMEM_TOK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SMEM_BAR);
+  uint64_t* w_full = bars;                         // packed weights (+ s2) landed                       (1 arrival + tx)
+  uint64_t* w_empty = w_full + C::W_STAGES;        // the four unpack warps of the owning set read it      (4)
+  uint64_t* b_full = w_empty + C::W_STAGES;        // activation tile landed                              (1 + tx)
+  uint64_t* a_full = b_full + AB_STAGES;           // the four unpack warps filled the TMEM A slot         (4)
+  uint64_t* ba_empty = a_full + AB_STAGES;         // MMAs that read activation stage s / A slot s retired (1, commit)
+  uint64_t* acc_full = ba_empty + AB_STAGES;       // last MMA of the segment retired                      (1, commit)
+  uint64_t* acc_empty = acc_full + 1;              // the eight epilogue warps drained the accumulator     (8)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::SMEM_MISC);
+  int* sFlag = reinterpret_cast<int*>(smem + C::SMEM_MISC + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) { tma_prefetch_desc(&act_map); tma_prefetch_desc(&w_map); }
+    for (int i = lane; i < C::NUM_BARS; i += 32) {
+      uint64_t* b = bars + i;
+      const uint32_t cnt = ((b >= w_empty && b < b_full) || (b >= a_full && b < ba_empty)) ? 4u : (b == acc_empty ? 8u : 1u);
+      mbar_init(b, cnt);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ weight producer: never waits for the previous
+    // kernel (weights are constants), so under PDL it fills the ring while the predecessor is still draining
+    if (lane == 0) {
+      SegIter it; it.init(p);
+      Seg sg;
+      int stage = 0, phase = 0;
+      OB_T_DECL(1);
+      while (it.next(sg)) {
+        const int n_cnt = min(BM, p.N - sg.tile * BM);
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          OB_T(0, mbar_wait(&w_empty[stage], phase ^ 1));
+          mbar_arrive_expect_tx(&w_full[stage], W_STAGE + (PER_GROUP ? 2 * n_cnt : 0));
+          tma_load_3d(sW + stage * W_STAGE, &w_map, 0, kb * 4, sg.tile * 4, &w_full[stage]);
+          if (PER_GROUP) {
+            bulk_g2s(sS2 + stage * S2_STAGE, p.s2_scales + (size_t)kb * p.N + sg.tile * BM, n_cnt, &w_full[stage]);
+            bulk_g2s(sS2 + stage * S2_STAGE + 128, p.s2_zeros + (size_t)kb * p.N + sg.tile * BM, n_cnt, &w_full[stage]);
+          }
+          if (++stage == C::W_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      OB_T_DUMP(p.dbg_t[blockIdx.x * 32 + 0] = tw[0]);
+    }
+  } else if (warp == 1) {
+    // ================================================================ activation producer (previous kernel's output)
+    if (lane == 0) {
+      pdl_wait();
+      SegIter it; it.init(p);
+      Seg sg;
+      int stage = 0, phase = 0;
+      OB_T_DECL(1);
+      while (it.next(sg)) {
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          OB_T(0, mbar_wait(&ba_empty[stage], phase ^ 1));
+          mbar_arrive_expect_tx(&b_full[stage], C::B_STAGE);
+          tma_load_2d(sB + stage * C::B_STAGE, &act_map, kb * BK, 0, &b_full[stage]);
+          if (++stage == AB_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      OB_T_DUMP(p.dbg_t[blockIdx.x * 32 + 1] = tw[0]);
+    }
+  } else if (warp == 2) {
+    // ================================================================ MMA issuer
+    SegIter it; it.init(p);
+    Seg sg;
+    int st = 0, ph = 0, acc_phase = 0;
+    constexpr uint32_t idesc = umma_idesc_i8(BM, BN, true, true);
+    const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(sB));
+    const uint32_t a_tmem0 = tmem_base + ACC_COLS;
+    OB_T_DECL(5);
+#ifdef OB_DEC_TIMING
+    const long long t_start = clock64();
+#endif
+    while (it.next(sg)) {
+      OB_T(0, mbar_wait(acc_empty, acc_phase ^ 1));
+      tc_fence_after();
+      for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+        OB_T(1, mbar_wait(&b_full[st], ph));
+        OB_T(2, mbar_wait(&a_full[st], ph));
+        tc_fence_after();
+#ifdef OB_DEC_TIMING
+        const long long t_i = clock64();
+#endif
+        if (elect_one()) {
+          const uint64_t bdesc = bdesc0 + (uint64_t)((st * C::B_STAGE) >> 4);
+          const uint32_t a_tmem = a_tmem0 + st * A_COLS;
+          umma_i8_ts(tmem_base, a_tmem, bdesc, idesc, kb > sg.kb0 ? 1u : 0u);
+          umma_i8_ts(tmem_base, a_tmem + 8, bdesc + 2, idesc, 1u);
+          umma_i8_ts(tmem_base, a_tmem + 16, bdesc + 4, idesc, 1u);
+          umma_i8_ts(tmem_base, a_tmem + 24, bdesc + 6, idesc, 1u);
+#ifdef OB_DEC_TIMING
+          tw[3] += clock64() - t_i;
+#endif
+          umma_commit(&ba_empty[st]);
+          if (kb == sg.kb1 - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+#ifdef OB_DEC_TIMING
+        tw[4] += clock64() - t_i;
+#endif
+        if (++st == AB_STAGES) { st = 0; ph ^= 1; }
+      }
+      acc_phase ^= 1;
+    }
+    OB_T_DUMP(if (lane == 0) { for (int i = 0; i < 5; ++i) p.dbg_t[blockIdx.x * 32 + 2 + i] = tw[i]; p.dbg_t[blockIdx.x * 32 + 7] = clock64() - t_start; });
+  } else if (warp >= 4) {
+    // ================================================================ unpack (two sets alternating K-blocks) + epilogue
+    const int set = (warp - 4) >> 2;       // 0: even K-blocks of this CTA's sequence, 1: odd
+    const int q = warp & 3;                // TMEM lane quarter == n32 block inside the tile
+    const int et = threadIdx.x - 128;      // 0..255
+    SegIter it; it.init(p);
+    Seg sg;
+    const uint32_t sW_u32 = smem_u32(sW), sS2_u32 = smem_u32(sS2);
+    const uint32_t t_q = tmem_base + ((uint32_t)(q * 32) << 16);
+    int idx = 0;                           // running K-block index of this CTA (all segments)
+    int acc_phase = 0;
+    bool waited = false;
+    OB_T_DECL(8);
+
+    while (it.next(sg)) {
+      // ---------------------------------------------------------------- unpack this set's K-blocks of the segment
+      for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++idx) {
+        if ((idx & 1) != set) continue;
+        const int ws = idx % C::W_STAGES, wph = (idx / C::W_STAGES) & 1;
+        const int as = idx % AB_STAGES, aph = (idx / AB_STAGES) & 1;
+        OB_T(0, mbar_wait(&w_full[ws], wph));
+#ifdef OB_DEC_TIMING
+        const long long t_a = clock64();
+#endif
+        uint4 v[4];
+        const uint32_t wsm = sW_u32 + ws * W_STAGE + q * 2048 + lane * 16;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) v[a] = lds_v4(wsm + a * 512);
+        uint32_t sc[4], zr[4];
+        if (PER_GROUP) {
+          const uint32_t ps = lds_u32(sS2_u32 + ws * S2_STAGE + q * 32 + (lane >> 2) * 4);
+          const uint32_t pz = lds_u32(sS2_u32 + ws * S2_STAGE + 128 + q * 32 + (lane >> 2) * 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sc[j] = (ps >> (8 * j)) & 0xFFu;
+            zr[j] = ((pz >> (8 * j)) & 0xFFu) * 0x01010101u;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&w_empty[ws]);     // the packed stage is in registers: hand it back right away
+#ifdef OB_DEC_TIMING
+        tw[5] += clock64() - t_a;
+#endif
+        OB_T(1, mbar_wait(&ba_empty[as], aph ^ 1));   // MMAs that read the slot's previous contents retired
+        tc_fence_after();
+#ifdef OB_DEC_TIMING
+        const long long t_b = clock64();
+#endif
+        const uint32_t t_lo = t_q + ACC_COLS + as * A_COLS;
+        const uint32_t t_hi = t_lo + (16u << 16);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          uint32_t l0 = v[a].x & 0x0F0F0F0Fu, l1 = v[a].y & 0x0F0F0F0Fu, l2 = v[a].z & 0x0F0F0F0Fu, l3 = v[a].w & 0x0F0F0F0Fu;
+          uint32_t h0 = (v[a].x >> 4) & 0x0F0F0F0Fu, h1 = (v[a].y >> 4) & 0x0F0F0F0Fu, h2 = (v[a].z >> 4) & 0x0F0F0F0Fu,
+                   h3 = (v[a].w >> 4) & 0x0F0F0F0Fu;
+          if (PER_GROUP) {
+            // rows: l0,l2 -> c (scale 0); l1,l3 -> c+8 (scale 1); h0,h2 -> c+16 (scale 2); h1,h3 -> c+24 (scale 3)
+            l0 = vadd4(l0 * sc[0], zr[0]); l2 = vadd4(l2 * sc[0], zr[0]);
+            l1 = vadd4(l1 * sc[1], zr[1]); l3 = vadd4(l3 * sc[1], zr[1]);
+            h0 = vadd4(h0 * sc[2], zr[2]); h2 = vadd4(h2 * sc[2], zr[2]);
+            h1 = vadd4(h1 * sc[3], zr[3]); h3 = vadd4(h3 * sc[3], zr[3]);
+          }
+          tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
+          tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
+        }
+#ifdef OB_DEC_TIMING
+        tw[6] += clock64() - t_b;
+#endif
+        OB_T(2, tmem_st_wait());   // the other set is converting the next K-block meanwhile
+#ifdef OB_DEC_TIMING
+        const long long t_c = clock64();
+#endif
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[as]);
+#ifdef OB_DEC_TIMING
+        tw[7] += clock64() - t_c;
+#endif
+      }
+
+      // ---------------------------------------------------------------- epilogue of the segment (all eight warps)
+      if (!waited) { pdl_wait(); waited = true; }   // ascales / a_ssums, `out` and the workspace belong to the chain
+      const int nt = sg.tile;
+      const int n_row = nt * BM + q * 32 + lane;
+      const bool n_ok = n_row < p.N;
+      const bool full_tile = (sg.kb0 == 0 && sg.kb1 == p.kb_per_tile);
+      float wsc = 0.f, wsz = 0.f;
+      if (n_ok) {
+        wsc = __half2float(p.wscales[n_row]);
+        if (!PER_GROUP) wsz = __half2float(p.w_szs[n_row]);
+      }
+      if (et < BN) {
+        sTok[et] = (et < p.M) ? __half2float(p.ascales[et]) : 0.f;
+        sTok[BN + et] = (!PER_GROUP && et < p.M) ? __half2float(p.a_ssums[et]) : 0.f;
+      }
+      OB_T(3, mbar_wait(acc_full, acc_phase));
+      acc_phase ^= 1;
+#ifdef OB_DEC_TIMING
+      const long long t_epi0 = clock64();
+#endif
+      tc_fence_after();
+      bar_epi();   // sTok visible
+      constexpr int HALF = BN / 2;                       // tokens per set
+      constexpr int CH = HALF >= 16 ? 16 : 8;            // columns per tcgen05.ld
+      const int c_base = set * HALF;
+      const int first_cta = (int)(((long long)nt * p.kb_per_tile) / p.units_per_cta);
+      int32_t* slot = p.ws + (size_t)first_cta * (BN * BM);
+#pragma unroll 1
+      for (int c0 = c_base; c0 < c_base + HALF; c0 += CH) {
+        uint32_t r[16];
+        if (CH == 16) {
+          tmem_ld_32x32b_x16(t_q + c0, r);
+        } else {
+          uint32_t r8[8];
+          tmem_ld_32x32b_x8(t_q + c0, r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = r8[j];
+        }
+        tmem_ld_wait();
+        if (full_tile) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int m = c0 + j;
+            const float ps = __int2float_rn((int)r[j]);
+            float o;
+            if (PER_GROUP) o = ps * (wsc * sTok[m]);
+            else o = __fmaf_rn(-wsz, sTok[BN + m], (ps * wsc) * sTok[m]);
+            if (n_ok && m < p.M) p.out[(size_t)m * p.ldc + n_row] = __float2half_rn(o);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) red_add_s32(slot + (c0 + j) * BM + q * 32 + lane, (int)r[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);    // MMAs of the next segment may overwrite the accumulator
+      if (!full_tile) {
+        // exact INT32 split-K: every contributor's reds must be performed before its arrival is counted
+        const int last_cta = (int)(((long long)(nt + 1) * p.kb_per_tile - 1) / p.units_per_cta);
+        const int contributors = last_cta - first_cta + 1;
+        __threadfence();
+        bar_epi();
+        if (et == 0) {
+          const int old = atomicAdd(&p.counters[first_cta], 1);
+          *sFlag = (old == contributors - 1) ? 1 : 0;
+        }
+        bar_epi();
+        if (*sFlag) {
+          __threadfence();
+          // finalize: thread (q, lane, set) owns row n_row and the tokens of its set; L2 reads are batched
+          constexpr int BATCH = HALF < 16 ? HALF : 16;
+#pragma unroll 1
+          for (int c0 = c_base; c0 < c_base + HALF; c0 += BATCH) {
+            int a[BATCH];
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) a[j] = __ldcg(slot + (c0 + j) * BM + q * 32 + lane);
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+              const int m = c0 + j;
+              __stcg(slot + m * BM + q * 32 + lane, 0);
+              const float ps = __int2float_rn(a[j]);
+              float o;
+              if (PER_GROUP) o = ps * (wsc * sTok[m]);
+              else o = __fmaf_rn(-wsz, sTok[BN + m], (ps * wsc) * sTok[m]);
+              if (n_ok && m < p.M) p.out[(size_t)m * p.ldc + n_row] = __float2half_rn(o);
+            }
+          }
+          if (et == 0) p.counters[first_cta] = 0;
+        }
+      }
+      bar_epi();   // sTok / sFlag free for the next segment
+#ifdef OB_DEC_TIMING
+      tw[4] += clock64() - t_epi0;
+#endif
+    }
+    OB_T_DUMP(if (lane == 0 && q == 0) { for (int i = 0; i < 8; ++i) p.dbg_t[blockIdx.x * 32 + 8 + set * 8 + i] = tw[i]; });
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int BN, bool PG>
+static int launch(const CUtensorMap& amap, const CUtensorMap& wmap, const Params& p, int grid, cudaStream_t st) {
+  using C = Cfg<BN>;
+  auto kern = w4a8_gemm_decode_kernel<BN, PG>;
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL) != cudaSuccess) return OB_ERR_CUDA;
+    attr_done[dev] = true;
+  }
+  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, amap, wmap, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
+}
+
+}  // namespace dec
+
+// Scheduling: every CTA gets `upc` consecutive (tile, K-block) units.  A CTA whose range stays inside one tile runs one
+// epilogue, one that crosses a tile boundary runs two (or more), and a split tile costs a finalisation, so ranges aligned
+// to the tiles are preferred when they cost little parallelism:  cost(upc) = upc * T_KB + segments(upc) * T_EPI.
+static int choose_upc(int n_tiles, int KB, int max_ctas) {
+  const long long units = (long long)n_tiles * KB;
+  const int lo = (int)((units + max_ctas - 1) / max_ctas);
+  const float T_KB = 0.20f, T_EPI = 0.9f;
+  int best = lo;
+  float best_cost = 1e30f;
+  for (int upc = lo; upc <= KB && upc <= 2 * lo + 4; ++upc) {
+    const int segs = (KB % upc == 0) ? 1 : ((upc < KB) ? 2 : 1 + (upc + KB - 1) / KB);
+    const float cost = upc * T_KB + segs * T_EPI + ((KB % upc == 0 && upc == KB) ? -0.5f * T_EPI : 0.f);
+    if (cost < best_cost - 1e-6f) { best_cost = cost; best = upc; }
+  }
+  if (lo > KB) return lo;   // more than a tile per CTA: plain stream-K
+  return best;
+}
+
+int w4a8_gemm_decode_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st) {
+  using namespace dec;
+  if (a.M <= 0) return 0;
+  if (a.M > 64 || a.N % 32 != 0 || a.K % 128 != 0 || a.ldc < a.N || a.tail_hidden_in) return OB_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(a.in_feats) & 15) || (reinterpret_cast<uintptr_t>(a.qweight) & 15)) return OB_ERR_ALIGN;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return OB_ERR_ARG;
+  const int sms = dev_sms(dev);
+  int32_t* ws = nullptr;
+  int32_t* cnt = nullptr;
+  if (int e = get_workspace(dev, st, &ws, &cnt)) return e;
+
+  int BN = a.M <= 16 ? 16 : a.M <= 32 ? 32 : 64;
+  if (a.force_bn == 16 || a.force_bn == 32 || a.force_bn == 64) BN = std::max(BN, a.force_bn);
+  Params p{};
+  p.s2_scales = a.s2_scales; p.s2_zeros = a.s2_zeros;
+  p.wscales = a.wscales; p.ascales = a.ascales; p.w_szs = a.w_szs; p.a_ssums = a.a_ssums;
+  p.out = a.out_feats; p.ws = ws; p.counters = cnt;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.ldc = a.ldc;
+  p.n_tiles = (a.N + BM - 1) / BM;
+  p.kb_per_tile = a.K / BK;
+#ifdef OB_DEC_TIMING
+  { const char* e = getenv("OB_DEC_DBGT"); p.dbg_t = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr; }
+#endif
+  static const int ctas_per_sm = [] { const char* e = getenv("OB_GEMM_DEC_CTAS_PER_SM"); return e ? std::max(1, std::min(2, atoi(e))) : 2; }();
+  int max_ctas = a.force_ctas > 0 ? std::min(a.force_ctas, 2 * sms) : ctas_per_sm * sms;
+  const long long units = (long long)p.n_tiles * p.kb_per_tile;
+  p.units_per_cta = a.force_ctas > 0 ? (int)((units + max_ctas - 1) / max_ctas) : choose_upc(p.n_tiles, p.kb_per_tile, max_ctas);
+  const int grid = (int)((units + p.units_per_cta - 1) / p.units_per_cta);
+  CUtensorMap amap, wmap;
+  if (int e = make_act_map(&amap, a.in_feats, a.M, a.K, BN)) return e;
+  if (int e = make_w_map(&wmap, a.qweight, a.N, a.K, false)) return e;
+  switch (BN) {
+    case 16: return per_group ? launch<16, true>(amap, wmap, p, grid, st) : launch<16, false>(amap, wmap, p, grid, st);
+    case 32: return per_group ? launch<32, true>(amap, wmap, p, grid, st) : launch<32, false>(amap, wmap, p, grid, st);
+    default: return per_group ? launch<64, true>(amap, wmap, p, grid, st) : launch<64, false>(amap, wmap, p, grid, st);
+  }
+}
+
+}  // namespace ob

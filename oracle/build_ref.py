@@ -44,6 +44,7 @@ FA = "fused_attention"
 MODULES = {
     "qgemm_w4a8_per_chn": ["qgemm/w4a8_per_chn/pybind.cpp", "qgemm/w4a8_per_chn/gemm_cuda.cu"],
     "qgemm_w4a8_per_group": ["qgemm/w4a8_per_group/pybind.cpp", "qgemm/w4a8_per_group/gemm_cuda.cu"],
+    "qgemm_w8a8": ["qgemm/w8a8/pybind.cpp", "qgemm/w8a8/w8a8_gemm_cuda.cu"],
     "fused_kernels": ["fused.cpp", "fused_kernels.cu"],
     "layernorm_ops": ["layernorm.cpp", "layernorm_kernels.cu"],
     "activation_ops": ["activation.cpp", "activation_kernels.cu"],

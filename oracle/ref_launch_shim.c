@@ -6,7 +6,9 @@
  * (sparse_utils/KVPageSelector/KVPageSelectorTemplate.hpp:1345-1347 `smem_size_in_bytes` returns 0) while the kernel
  * stages the rotated query through `extern __shared__ char smem_[]` (`q_smem_`, :1001-1053: rotary_dim halves = 256 B).
  * Those stores land beyond the CTA's shared-memory window; on sm_100 the window is enforced and the launch dies with
- * "illegal memory access" (observed on B200 in round 1, confirmed with compute-sanitizer in round 2).  The reference
+ * "illegal memory access" (observed on B200 in round 1; compute-sanitizer in round 2: "Invalid __shared__ write of size
+ * 8 bytes ... Access at 0x580 is out of bounds", 0x580 = the kernel's 1408 B of static shared memory,
+ * profiles/r2_selector_memcheck.log).  The reference
  * sources stay untouched: this shim adds OB_REF_EXTRA_SMEM bytes (default 1024) of dynamic shared memory to kernel
  * launches that ask for none, which is what a correct `smem_size_in_bytes` would have requested.
  *

@@ -195,6 +195,19 @@ def gemm_per_group(in_feats, qweight, zeros_i8, scales_i8, wscales, ascales, gro
 # ----------------------------------------------------------------------------------------------
 # BASELINE config 1: per-channel quant -> pack -> unpack -> dequant round trip
 # ----------------------------------------------------------------------------------------------
+def gemm_w8a8(in_feats, weight, wscales, ascales):
+    """W8A8 GEMM of kernels/csrc/qgemm/w8a8/w8a8_gemm_cuda.cu:515-530: ``C = rn_f16( f32(A . W^T) * (ws[n] * as[m]) )`` with
+    the scale product formed first in fp32 (``psum *= wscale * ascale``).  in_feats int8 [M,K], weight int8 [N,K] row-major.
+    Returns (acc int32 [M,N], out float16 [M,N])."""
+    a = np.asarray(in_feats, np.int8)
+    w = np.asarray(weight, np.int8)
+    acc = _exact_int_gemm(a, w.astype(np.int32))
+    ws = np.asarray(wscales, np.float16).astype(np.float32)[None, :]
+    sa = np.asarray(ascales, np.float16).astype(np.float32)[:, None]
+    out = (acc.astype(np.float32) * (ws * sa).astype(np.float32)).astype(np.float32)
+    return acc, out.astype(np.float16)
+
+
 def roundtrip_per_channel(w: np.ndarray):
     """Returns (w_fake, w_roundtrip, packed).  ``w_roundtrip`` must equal ``w_fake`` exactly."""
     w_fake, scales, zeros = pseudo_quantize_tensor(w, n_bit=4, q_group_size=-1)

@@ -102,7 +102,7 @@ def test_streaming_heads_sink_plus_local_ring(lens):
         assert (kpool2 != kpool).float().mean() < 1e-3
 
 
-@pytest.mark.parametrize("lens,P", [((700, 300), 4), ((1281, 1025), 9), ((64, 65), 1)])
+@pytest.mark.parametrize("lens,P", [((700, 300), 4), ((1281, 1025), 9), ((64, 65), 1), ((2100, 2300), 4), ((4500, 4400), 9)])
 def test_dynamic_page_selection(lens, P):
     from omniserve_b200.backend import fused_attention_fine_grained_sparse as op
     from oracle import kv4
@@ -128,7 +128,7 @@ def test_dynamic_page_selection(lens, P):
     _, tq, tk, tv = qkv_views(q, k, v)
     flags = t(np.ones(Hkv, np.int32))
     rank = t(np.arange(Hkv, dtype=np.int32))
-    out = op.single_query_attention(tq, tk, tv, ptrs, None, flags, rank, t(dyn), t(np.asarray(lens, np.int32)), None, 4096,
+    out = op.single_query_attention(tq, tk, tv, ptrs, None, flags, rank, t(dyn), t(np.asarray(lens, np.int32)), None, 8192,
                                     64, Hkv * 64, 0, 0, 0, 0, 0, Hkv, 0, max(lens) - 1, 128, 500000.0, 1.0, True, True, True,
                                     16, Hkv * 128, 2048)
     torch.cuda.synchronize()
@@ -149,10 +149,14 @@ def test_dynamic_page_selection(lens, P):
     assert_k_pool_equal(kpool, cache)   # nibbles, scales, zeros exact; kmax / kmin to the last fp16 bits
     np.testing.assert_array_equal(vpool.cpu().numpy(), cache.v_pool)
     rm = ref_module("fused_attention_fine_grained_sparse")
-    if rm is not None:
+    # The reference dispatches its SMEM_PRELOAD variant below timestep 2048 (sparse_attention/fused_attention.cpp:
+    # smem_preload_switch), whose K loop asserts tokens_per_block % 128 == 0 -- with 64-token pages it can only run its
+    # dynamic-page path at timestep >= 2048 (LServe only selects pages beyond the 4096-token budget anyway).
+    if rm is not None and max(lens) - 1 >= 2048:
         cache.k_pool[:], cache.v_pool[:] = pools0
         kpool2, vpool2, ptrs2 = device_tables(cache, bt)
-        o2 = rm.single_query_attention(tq, tk, tv, ptrs2, None, flags, rank, t(dyn), t(np.asarray(lens, np.int32)), None, 4096,
+        # memory_max_seqlen must cover the context (the reference sizes its logits buffer from it)
+        o2 = rm.single_query_attention(tq, tk, tv, ptrs2, None, flags, rank, t(dyn), t(np.asarray(lens, np.int32)), None, 8192,
                                        64, Hkv * 64, 0, 0, 0, 0, 0, Hkv, 0, max(lens) - 1, 128, 500000.0, 1.0, True, True,
                                        True, 16, Hkv * 128, 2048)
         torch.cuda.synchronize()

@@ -74,3 +74,62 @@ def test_whole_stack_vs_reference_kernels():
     r = ref.decode_step(t, 192)
     hr = ref.last_decode_state[0].float() + ref.last_decode_state[1].float()
     assert (ho - hr).abs().max() <= 3e-2 * hr.abs().max()
+
+
+def test_reference_op_chain_equals_fused_production_path_bit_for_bit():
+    """GPU half of the boundary proof (tests/test_ref_callers_cpu.py is the CPU half): model.py restricted to the
+    reference's op set issues the call sequence recorded from the reference's own LlamaDecoderLayer
+    (tests/golden/ref_layer_trace.json), and its results -- prefill hidden states, sampled ids, KV pages, decode hidden
+    states -- equal the fused production path (add+norm+quant, silu*mul+quant, attention+quant in one launch each) bit for bit."""
+    import json
+    import os
+    from omniserve_b200 import _lib as L
+    from tests.ref_trace_worker import ReferenceOpsOnly
+    cfg, fused = _mk()
+    cfg, plain = _mk(ops=ReferenceOpsOnly(), fuse=False)
+    assert fused.fuse_add_norm and fused.fuse_attn_quant and not plain.fuse_add_norm and not plain.fuse_attn_quant
+    toks, lens = _prompts(cfg)
+    # record the C-ABI entry points the unfused path goes through (pass-through wrapper around the real library)
+    real, names = L.lib(), []
+
+    class Tap:
+        def __getattr__(self, n):
+            f = getattr(real, n)
+            if not n.startswith("ob_"):
+                return f
+
+            def g(*a):
+                names.append(n)
+                return f(*a)
+            return g
+    saved = L.lib
+    L.lib = lambda: Tap()
+    try:
+        b = plain.prefill(toks, lens)
+        n_prefill = len(names)
+        plain.prepare_decode()
+        tb = plain.decode_step(b.clone(), 192)
+    finally:
+        L.lib = saved
+    a = fused.prefill(toks, lens)
+    assert torch.equal(a, b) and torch.equal(fused.last_hidden, plain.last_hidden)
+    for x, y in zip(fused.kv.k_pools + fused.kv.v_pools, plain.kv.k_pools + plain.kv.v_pools):
+        assert torch.equal(x, y)
+    fused.prepare_decode()
+    ta = fused.decode_step(a.clone(), 192)
+    torch.cuda.synchronize()
+    assert torch.equal(ta, tb)
+    ha = fused.last_decode_state[0].float() + fused.last_decode_state[1].float()
+    hb = plain.last_decode_state[0].float() + plain.last_decode_state[1].float()
+    assert torch.equal(ha, hb)
+    for x, y in zip(fused.kv.k_pools + fused.kv.v_pools, plain.kv.k_pools + plain.kv.v_pools):
+        assert torch.equal(x, y)
+    # per layer, the unfused path's entry points are those of the reference's own layer, in order
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_layer_trace.json")))["traces"]
+    per_layer_prefill = [c[0] for c in fx["prefill"]["calls"]]
+    per_layer_decode = [c[0] for c in fx["decode"]["calls"]]
+    L_ = cfg.num_hidden_layers
+    pre = [n for n in names[:n_prefill] if n not in ("ob_compute_padding_offsets", "ob_rms_norm")]
+    dec = [n for n in names[n_prefill:] if n != "ob_rms_norm"]
+    assert pre == per_layer_prefill * L_, pre
+    assert dec == per_layer_decode * L_, dec

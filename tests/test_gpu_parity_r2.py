@@ -42,7 +42,10 @@ def _launch(per_group, a, qw, z2, s2, s1, sa, szs, ssum, M, N, K, bn, mode, ctas
     return out.cpu().numpy()
 
 
-SCHEDULES = [(0, -1, 0), (0, 0, 0), (0, 1, 0), (0, 1, 37), (0, 2, 2), (0, 2, 4), (0, 2, 8), (16, 1, 148), (128, 0, 5)]
+# (force_bn, force_mode, force_ctas): -1 auto, 0 data-parallel tiles, 1 stream-K (L2 bulk reduce), 2 cluster split-K (DSMEM),
+# 3 decode kernel (w4a8_gemm_decode.cu: red.global.add.s32 split-K), M <= 64 only
+SCHEDULES = [(0, -1, 0), (0, 0, 0), (0, 1, 0), (0, 1, 37), (0, 2, 2), (0, 2, 4), (0, 2, 8), (16, 1, 148), (128, 0, 5),
+             (0, 3, 0), (0, 3, 37), (0, 3, 296), (64, 3, 100), (0, 3, 1)]
 
 
 @pytest.mark.parametrize("M,N,K", [(64, 4096, 4096), (64, 512, 14336), (17, 256, 2048), (200, 1024, 1024)])
@@ -57,7 +60,7 @@ def test_int32_accumulators_exact_per_channel(M, N, K):
     want = (a.astype(np.int64) @ q.astype(np.int64).T).astype(np.int32)
     assert np.abs(want).max() <= 2048
     for bn, mode, ctas in SCHEDULES:
-        if mode == 2 and (K // 128) < ctas:
+        if (mode == 2 and (K // 128) < ctas) or (mode == 3 and M > 64):
             continue
         got = _launch(False, a, qw, None, None, ones_n, ones_m, zero_n, junk_m, M, N, K, bn, mode, ctas)
         np.testing.assert_array_equal(got.astype(np.int32), want, err_msg=f"schedule bn={bn} mode={mode} ctas={ctas}")
@@ -83,7 +86,7 @@ def test_int32_accumulators_exact_per_group_with_byte_wrap(M, N, K):
     assert np.abs(want).max() <= 2048
     ones_n, ones_m = np.ones(N, np.float16), np.ones(M, np.float16)
     for bn, mode, ctas in SCHEDULES:
-        if mode == 2 and (K // 128) < ctas:
+        if (mode == 2 and (K // 128) < ctas) or (mode == 3 and M > 64):
             continue
         got = _launch(True, a, qw, z2p, s2p, ones_n, ones_m, None, None, M, N, K, bn, mode, ctas)
         np.testing.assert_array_equal(got.astype(np.int32), want, err_msg=f"schedule bn={bn} mode={mode} ctas={ctas}")

@@ -103,3 +103,17 @@ def test_per_group_wraparound_is_modelled():
     word = (0x0F0F0F0F * 20) & 0xFFFFFFFF
     expect = [(((word >> (8 * i)) & 0xFF) + ((-3 * 20) & 0xFF)) & 0xFF for i in range(4)]
     np.testing.assert_array_equal(w8[0, :4], expect)
+
+
+def test_w8a8_oracle_matches_plain_definition():
+    """oracle.w4a8.gemm_w8a8: exact INT32 accumulate, fp32 scale product formed first (w8a8_gemm_cuda.cu:527-529)."""
+    from oracle import w4a8 as ow
+    rng = np.random.default_rng(0)
+    a = rng.integers(-127, 128, (5, 256), dtype=np.int8)
+    w = rng.integers(-127, 128, (24, 256), dtype=np.int8)
+    ws = rng.uniform(0.002, 0.01, 24).astype(np.float16)
+    sa = rng.uniform(0.01, 0.05, 5).astype(np.float16)
+    acc, out = ow.gemm_w8a8(a, w, ws, sa)
+    np.testing.assert_array_equal(acc, a.astype(np.int64) @ w.astype(np.int64).T)
+    want = (acc.astype(np.float32) * (ws.astype(np.float32)[None, :] * sa.astype(np.float32)[:, None])).astype(np.float16)
+    np.testing.assert_array_equal(out, want)

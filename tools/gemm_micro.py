@@ -47,6 +47,67 @@ def run(M, N, K, mode=-1, bn=0, ctas=0, tag=""):
           f"{by / us / 1e3:8.1f} GB/s  {2.0 * M * N * K / us / 1e6:8.1f} TOPS", flush=True)
 
 
+def chain(M, shapes, mode, ctas, layers=8, tag=""):
+    """The four GEMMs of `layers` decoder layers back to back in ONE graph (PDL-chained, distinct weights per layer):
+    what the decode step's GEMMs cost when each launch can overlap its predecessor's tail."""
+    ws = [[torch.randint(-128, 128, (N, K // 2), dtype=torch.int8, device=dev) for (N, K) in shapes] for _ in range(layers)]
+    Kmax, Nmax = max(k for _, k in shapes), max(n for n, _ in shapes)
+    x = torch.randint(-127, 128, (M, Kmax), dtype=torch.int8, device=dev)
+    s1 = torch.full((Nmax,), 0.01, dtype=torch.float16, device=dev)
+    sz = torch.full((Nmax,), 0.08, dtype=torch.float16, device=dev)
+    sa = torch.full((M,), 0.02, dtype=torch.float16, device=dev)
+    ss = torch.full((M,), 0.1, dtype=torch.float16, device=dev)
+    outs = [torch.empty((M, N), dtype=torch.float16, device=dev) for (N, K) in shapes]
+    xs = [x[:, :K].contiguous() for (N, K) in shapes]
+
+    def launch_all():
+        for l in range(layers):
+            for i, (N, K) in enumerate(shapes):
+                c = L.lib().ob_w4a8_gemm_ex(0, L.ptr(xs[i]), L.ptr(ws[l][i]), 0, 0, L.ptr(s1), L.ptr(sa), L.ptr(sz), L.ptr(ss),
+                                            L.ptr(outs[i]), M, N, K, N, 0, mode, ctas, L.stream())
+                assert c == 0
+    launch_all()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        launch_all()
+    best = 1e9
+    for _ in range(5):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    us = best / layers * 1e3
+    by = sum(N * K // 2 for N, K in shapes)
+    print(f"{tag:34s} M={M:3d} mode={mode:2d} ctas={ctas:3d}: {us:8.2f} us per layer (4 GEMMs)  {by / us / 1e3:8.1f} GB/s", flush=True)
+
+
+if __name__ == "__main__" and os.environ.get("OB_DEC_EXP"):
+    LL = [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)]
+    names = ["qkv", "o_proj", "gate_up", "down"]
+    for M in (64, 16):
+        for (N, K), nm in zip(LL, names):
+            run(M, N, K, mode=1, tag=f"{nm} v1 stream-K")
+            run(M, N, K, mode=3, ctas=0, tag=f"{nm} v2 auto")
+            run(M, N, K, mode=3, ctas=148, tag=f"{nm} v2 148 CTAs")
+            run(M, N, K, mode=3, ctas=296, tag=f"{nm} v2 296 CTAs")
+    run(64, 18944, 14336, mode=0, tag="v1 148 tiles x 112 kb")
+    run(64, 18944, 14336, mode=3, ctas=148, tag="v2 148 x 112 kb")
+    run(64, 18944, 14336, mode=3, ctas=296, tag="v2 296 x 56 kb")
+    run(64, 18944, 128, mode=3, ctas=148, tag="v2 fixed cost (148 x 1 kb)")
+    run(64, 4096, 14336, mode=3, ctas=32, tag="v2 32 CTAs x 112 kb")
+    for M in (64,):
+        chain(M, LL, 1, 0, tag="layer chain v1 stream-K")
+        chain(M, LL, 3, 0, tag="layer chain v2 auto")
+        chain(M, LL, 3, 148, tag="layer chain v2 148")
+        chain(M, LL, 3, 296, tag="layer chain v2 296")
+    # TP=8 shards of the same layer (strong scaling: per-GPU shapes)
+    TP8 = [(768, 4096), (4096, 512), (3584, 4096), (4096, 1792)]
+    chain(64, TP8, 1, 0, tag="tp8 shard chain v1")
+    chain(64, TP8, 3, 0, tag="tp8 shard chain v2 auto")
+    sys.exit(0)
+
 if __name__ == "__main__" and os.environ.get("OB_2CTA_SWEEP"):
     for two in ("0", "1"):
         os.environ["OB_GEMM_2CTA"] = two
