@@ -58,10 +58,16 @@ struct Params {
   int32_t* counters;  // [grid]
   int M, N, K, ldc;
   int n_tiles, kb_per_tile, units_per_cta;
+  int dbg;            // -DOB_DEC_TIMING builds only: ablations (1 no MMA, 2 no tcgen05.st, 4 no activation TMA, 8 no lds)
   long long* dbg_t;   // -DOB_DEC_TIMING builds only (tools/dec_waits.py): [grid][16] cycles per role
 };
 
 // Per-role cycle counters (compile with -DOB_DEC_TIMING, run tools/dec_waits.py); compiled out by default.
+#ifdef OB_DEC_TIMING
+#define OB_ABL(mask) ((p.dbg & (mask)) != 0)
+#else
+#define OB_ABL(mask) false
+#endif
 #ifdef OB_DEC_TIMING
 #define OB_T(slot, call) do { const long long _t0 = clock64(); call; tw[slot] += clock64() - _t0; } while (0)
 #define OB_T_DECL(n) long long tw[n] = {}
@@ -100,6 +106,13 @@ OB_DEVICE uint32_t vadd4(uint32_t a, uint32_t b) {   // bytewise (a + b) mod 256
   return s ^ ((a ^ b) & 0x80808080u);
 }
 
+#ifdef OB_DEC_TIMING
+OB_DEVICE long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define OB_GT(slot) do { if (p.dbg_t && lane == 0) p.dbg_t[blockIdx.x * 32 + (slot)] = gtime(); } while (0)
+#else
+#define OB_GT(slot) (void)0
+#endif
+
 OB_DEVICE void red_add_s32(int32_t* addr, int32_t v) {
   asm volatile("red.global.add.s32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
@@ -128,6 +141,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
+  if (warp == 3) OB_GT(24);   // kernel entry
 
   if (warp == 0) {
     if (lane == 0) { tma_prefetch_desc(&act_map); tma_prefetch_desc(&w_map); }
@@ -143,6 +157,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 3) OB_GT(25);   // prologue done (barriers, TMEM)
 
   if (warp == 0) {
     // ================================================================ weight producer: never waits for the previous
@@ -178,8 +193,8 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       while (it.next(sg)) {
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           OB_T(0, mbar_wait(&ba_empty[stage], phase ^ 1));
-          mbar_arrive_expect_tx(&b_full[stage], C::B_STAGE);
-          tma_load_2d(sB + stage * C::B_STAGE, &act_map, kb * BK, 0, &b_full[stage]);
+          mbar_arrive_expect_tx(&b_full[stage], OB_ABL(4) ? 0 : C::B_STAGE);
+          if (!OB_ABL(4)) tma_load_2d(sB + stage * C::B_STAGE, &act_map, kb * BK, 0, &b_full[stage]);
           if (++stage == AB_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -201,8 +216,8 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       OB_T(0, mbar_wait(acc_empty, acc_phase ^ 1));
       tc_fence_after();
       for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-        OB_T(1, mbar_wait(&b_full[st], ph));
-        OB_T(2, mbar_wait(&a_full[st], ph));
+        if (!OB_ABL(64)) OB_T(1, mbar_wait(&b_full[st], ph));
+        if (!OB_ABL(128)) OB_T(2, mbar_wait(&a_full[st], ph));
         tc_fence_after();
 #ifdef OB_DEC_TIMING
         const long long t_i = clock64();
@@ -210,15 +225,22 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
         if (elect_one()) {
           const uint64_t bdesc = bdesc0 + (uint64_t)((st * C::B_STAGE) >> 4);
           const uint32_t a_tmem = a_tmem0 + st * A_COLS;
+          if (!OB_ABL(1)) {
           umma_i8_ts(tmem_base, a_tmem, bdesc, idesc, kb > sg.kb0 ? 1u : 0u);
           umma_i8_ts(tmem_base, a_tmem + 8, bdesc + 2, idesc, 1u);
           umma_i8_ts(tmem_base, a_tmem + 16, bdesc + 4, idesc, 1u);
           umma_i8_ts(tmem_base, a_tmem + 24, bdesc + 6, idesc, 1u);
+          }
 #ifdef OB_DEC_TIMING
           tw[3] += clock64() - t_i;
 #endif
+          if (OB_ABL(16)) {   // ablation: plain arrives instead of tcgen05.commit
+            mbar_arrive(&ba_empty[st]);
+            if (kb == sg.kb1 - 1) mbar_arrive(acc_full);
+          } else {
           umma_commit(&ba_empty[st]);
           if (kb == sg.kb1 - 1) umma_commit(acc_full);
+          }
         }
         __syncwarp();
 #ifdef OB_DEC_TIMING
@@ -255,8 +277,13 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
 #endif
         uint4 v[4];
         const uint32_t wsm = sW_u32 + ws * W_STAGE + q * 2048 + lane * 16;
+        if (!OB_ABL(8)) {
 #pragma unroll
         for (int a = 0; a < 4; ++a) v[a] = lds_v4(wsm + a * 512);
+        } else {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) v[a] = make_uint4(idx, a, lane, 7);
+        }
         uint32_t sc[4], zr[4];
         if (PER_GROUP) {
           const uint32_t ps = lds_u32(sS2_u32 + ws * S2_STAGE + q * 32 + (lane >> 2) * 4);
@@ -272,7 +299,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
 #ifdef OB_DEC_TIMING
         tw[5] += clock64() - t_a;
 #endif
-        OB_T(1, mbar_wait(&ba_empty[as], aph ^ 1));   // MMAs that read the slot's previous contents retired
+        if (!OB_ABL(32)) OB_T(1, mbar_wait(&ba_empty[as], aph ^ 1));   // MMAs that read the slot's previous contents retired
         tc_fence_after();
 #ifdef OB_DEC_TIMING
         const long long t_b = clock64();
@@ -291,8 +318,12 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
             h0 = vadd4(h0 * sc[2], zr[2]); h2 = vadd4(h2 * sc[2], zr[2]);
             h1 = vadd4(h1 * sc[3], zr[3]); h3 = vadd4(h3 * sc[3], zr[3]);
           }
+          if (!OB_ABL(2)) {
           tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
           tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
+          } else if (l0 + h3 == 0x12345u) {
+            tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
+          }
         }
 #ifdef OB_DEC_TIMING
         tw[6] += clock64() - t_b;
@@ -310,7 +341,12 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       }
 
       // ---------------------------------------------------------------- epilogue of the segment (all eight warps)
-      if (!waited) { pdl_wait(); waited = true; }   // ascales / a_ssums, `out` and the workspace belong to the chain
+      if (!waited) {   // ascales / a_ssums, `out` and the workspace belong to the chain
+        if (warp == 4) OB_GT(26);   // first segment unpacked
+        pdl_wait();
+        waited = true;
+        if (warp == 4) OB_GT(27);   // grid dependency resolved
+      }
       const int nt = sg.tile;
       const int n_row = nt * BM + q * 32 + lane;
       const bool n_ok = n_row < p.N;
@@ -325,6 +361,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
         sTok[BN + et] = (!PER_GROUP && et < p.M) ? __half2float(p.a_ssums[et]) : 0.f;
       }
       OB_T(3, mbar_wait(acc_full, acc_phase));
+      if (warp == 4) OB_GT(28);     // accumulator of the (last) segment complete
       acc_phase ^= 1;
 #ifdef OB_DEC_TIMING
       const long long t_epi0 = clock64();
@@ -401,6 +438,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
         }
       }
       bar_epi();   // sTok / sFlag free for the next segment
+      if (warp == 4) OB_GT(29);     // epilogue (incl. finalisation) of the (last) segment done
 #ifdef OB_DEC_TIMING
       tw[4] += clock64() - t_epi0;
 #endif
@@ -411,6 +449,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 3) OB_GT(30);   // exit
 }
 
 template <int BN, bool PG>
@@ -470,7 +509,13 @@ int w4a8_gemm_decode_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st)
   p.n_tiles = (a.N + BM - 1) / BM;
   p.kb_per_tile = a.K / BK;
 #ifdef OB_DEC_TIMING
-  { const char* e = getenv("OB_DEC_DBGT"); p.dbg_t = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr; }
+  {   // every launch gets its own [1024][32] block of the debug buffer (64 blocks, round robin)
+    static int launch_idx = 0;
+    const char* e = getenv("OB_DEC_DBGT");
+    p.dbg_t = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) + (size_t)(launch_idx++ % 64) * 1024 * 32 : nullptr;
+    const char* a2 = getenv("OB_DEC_DBG");
+    p.dbg = a2 ? atoi(a2) : 0;
+  }
 #endif
   static const int ctas_per_sm = [] { const char* e = getenv("OB_GEMM_DEC_CTAS_PER_SM"); return e ? std::max(1, std::min(2, atoi(e))) : 2; }();
   int max_ctas = a.force_ctas > 0 ? std::min(a.force_ctas, 2 * sms) : ctas_per_sm * sms;

@@ -94,9 +94,12 @@ def qkv_views(q, k, v):
             qkv[:, (Hq + Hkv) * Dh:].view(B, Hkv, Dh))
 
 
-def assert_k_pool_equal(got_pool, cache, max_stat_ulp=2, max_stat_frac=1e-3):
+def assert_k_pool_equal(got_pool, cache, max_stat_ulp=2, max_stat_frac=1e-3, max_pos=0):
     """K pages: nibbles, scales and zeros bit-exact; the kmax / kmin statistics (raw post-RoPE fp16 keys) may differ
-    from the numpy oracle in the last bits of a few elements (fp32 sincosf on the device vs numpy's libm)."""
+    from the numpy oracle in the last bits of a few elements (fp32 sincosf on the device vs numpy's libm).  The rotation
+    angle pos / base^(2i/d) is formed in fp32 on both sides, so a one-ulp difference between CUDA's powf and numpy's is
+    multiplied by the position: `max_pos` widens the ulp budget accordingly (1 ulp(fp32) * pos radians)."""
+    max_stat_ulp = max_stat_ulp + max_pos // 200
     got = got_pool.cpu().numpy() if hasattr(got_pool, "cpu") else got_pool
     cut = cache.data_bytes + cache.sz_bytes
     np.testing.assert_array_equal(got[:, :cut], cache.k_pool[:, :cut])

