@@ -20,7 +20,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--compiler-options", "-fPIC", "-Xptxas", "-v",
 ] + (["-DOB_GEMM_TIMING"] if os.environ.get("OB_GEMM_TIMING") == "1" else []) + (
-    ["-DOB_DEC_TIMING"] if os.environ.get("OB_DEC_TIMING") == "1" else [])  # per-role wait counters (tools/gemm_waits.py)
+    ["-DOB_DEC_TIMING"] if os.environ.get("OB_DEC_TIMING") == "1" else []) + (
+    [f"-DOB_DEC_KPS={os.environ['OB_DEC_KPS']}"] if os.environ.get("OB_DEC_KPS") else []) + (
+    ["-DOB_DEC_WAIT_FIRST"] if os.environ.get("OB_DEC_WAIT_FIRST") == "1" else [])  # per-role wait counters (tools/gemm_waits.py)
 
 
 def _newest_src() -> float:

@@ -26,19 +26,27 @@ namespace ob {
 namespace dec {
 
 constexpr int BM = 128;                  // weight rows per tile (UMMA M, TMEM lanes)
-constexpr int BK = 128;                  // K bytes per stage
-constexpr int W_STAGE = BM * BK / 2;     // 8 KB packed
-constexpr int S2_STAGE = 256;            // per-group: 128 B scales + 128 B zeros
+constexpr int BK = 128;                  // K bytes per K-block
+constexpr int W_KB = BM * BK / 2;        // 8 KB packed per K-block
+constexpr int S2_KB = 256;               // per-group: 128 B scales + 128 B zeros per K-block
 constexpr int NUM_THREADS = 384;
 constexpr int A_COLS = BK / 4;           // 32 TMEM columns per unpacked K-block
 constexpr int TMEM_COLS = 256;
 constexpr int ACC_COLS = 64;
-constexpr int AB_STAGES = (TMEM_COLS - ACC_COLS) / A_COLS;   // 6: TMEM A ring and activation ring advance in lock-step
+// A pipeline STEP is KPS consecutive K-blocks of one segment: every ring (packed weights, activations, TMEM A slots)
+// advances by steps, so the per-step handshakes (mbarrier waits / arrives, fences, commit) are paid once per KPS K-blocks.
+#ifndef OB_DEC_KPS
+#define OB_DEC_KPS 2
+#endif
+constexpr int KPS = OB_DEC_KPS;
+constexpr int AB_STAGES = (TMEM_COLS - ACC_COLS) / (A_COLS * KPS);   // 3 steps: TMEM A ring == activation ring depth
 
 template <int BN>
 struct Cfg {
-  static constexpr int W_STAGES = 6;
-  static constexpr int B_STAGE = BN * BK;
+  static constexpr int W_STAGES = BN <= 32 ? 5 : 3;                  // steps of packed weights in flight
+  static constexpr int W_STAGE = KPS * W_KB;
+  static constexpr int B_STAGE = KPS * BN * BK;
+  static constexpr int S2_STAGE = KPS * S2_KB;
   static constexpr int SMEM_B = 0;
   static constexpr int SMEM_W = SMEM_B + AB_STAGES * B_STAGE;
   static constexpr int SMEM_S2 = SMEM_W + W_STAGES * W_STAGE;
@@ -58,25 +66,8 @@ struct Params {
   int32_t* counters;  // [grid]
   int M, N, K, ldc;
   int n_tiles, kb_per_tile, units_per_cta;
-  int dbg;            // -DOB_DEC_TIMING builds only: ablations (1 no MMA, 2 no tcgen05.st, 4 no activation TMA, 8 no lds)
-  long long* dbg_t;   // -DOB_DEC_TIMING builds only (tools/dec_waits.py): [grid][16] cycles per role
+  long long* dbg_t;   // -DOB_DEC_TIMING builds only (tools/dec_waits.py): [grid][32] globaltimer stamps
 };
-
-// Per-role cycle counters (compile with -DOB_DEC_TIMING, run tools/dec_waits.py); compiled out by default.
-#ifdef OB_DEC_TIMING
-#define OB_ABL(mask) ((p.dbg & (mask)) != 0)
-#else
-#define OB_ABL(mask) false
-#endif
-#ifdef OB_DEC_TIMING
-#define OB_T(slot, call) do { const long long _t0 = clock64(); call; tw[slot] += clock64() - _t0; } while (0)
-#define OB_T_DECL(n) long long tw[n] = {}
-#define OB_T_DUMP(stmt) do { if (p.dbg_t) { stmt; } } while (0)
-#else
-#define OB_T(slot, call) call
-#define OB_T_DECL(n) (void)0
-#define OB_T_DUMP(stmt) (void)0
-#endif
 
 struct Seg { int tile, kb0, kb1; };
 
@@ -129,10 +120,10 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
   uint8_t* sS2 = smem + C::SMEM_S2;
   float* sTok = reinterpret_cast<float*>(smem + C::SMEM_TOK);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SMEM_BAR);
-  uint64_t* w_full = bars;                         // packed weights (+ s2) landed                       (1 arrival + tx)
-  uint64_t* w_empty = w_full + C::W_STAGES;        // the four unpack warps of the owning set read it      (4)
-  uint64_t* b_full = w_empty + C::W_STAGES;        // activation tile landed                              (1 + tx)
-  uint64_t* a_full = b_full + AB_STAGES;           // the four unpack warps filled the TMEM A slot         (4)
+  uint64_t* w_full = bars;                         // packed weights (+ s2) of the step landed              (1 arrival + tx)
+  uint64_t* w_empty = w_full + C::W_STAGES;        // the eight unpack warps read their K-blocks of the step (8)
+  uint64_t* b_full = w_empty + C::W_STAGES;        // activation tiles of the step landed                 (1 + tx)
+  uint64_t* a_full = b_full + AB_STAGES;           // the eight unpack warps filled the TMEM A slot        (8)
   uint64_t* ba_empty = a_full + AB_STAGES;         // MMAs that read activation stage s / A slot s retired (1, commit)
   uint64_t* acc_full = ba_empty + AB_STAGES;       // last MMA of the segment retired                      (1, commit)
   uint64_t* acc_empty = acc_full + 1;              // the eight epilogue warps drained the accumulator     (8)
@@ -141,13 +132,16 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
+#ifdef OB_DEC_WAIT_FIRST
+  pdl_wait();
+#endif
   if (warp == 3) OB_GT(24);   // kernel entry
 
   if (warp == 0) {
     if (lane == 0) { tma_prefetch_desc(&act_map); tma_prefetch_desc(&w_map); }
     for (int i = lane; i < C::NUM_BARS; i += 32) {
       uint64_t* b = bars + i;
-      const uint32_t cnt = ((b >= w_empty && b < b_full) || (b >= a_full && b < ba_empty)) ? 4u : (b == acc_empty ? 8u : 1u);
+      const uint32_t cnt = ((b >= w_empty && b < b_full) || (b >= a_full && b < ba_empty) || b == acc_empty) ? 8u : 1u;
       mbar_init(b, cnt);
     }
     mbar_fence_init();
@@ -166,21 +160,23 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       SegIter it; it.init(p);
       Seg sg;
       int stage = 0, phase = 0;
-      OB_T_DECL(1);
       while (it.next(sg)) {
         const int n_cnt = min(BM, p.N - sg.tile * BM);
-        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-          OB_T(0, mbar_wait(&w_empty[stage], phase ^ 1));
-          mbar_arrive_expect_tx(&w_full[stage], W_STAGE + (PER_GROUP ? 2 * n_cnt : 0));
-          tma_load_3d(sW + stage * W_STAGE, &w_map, 0, kb * 4, sg.tile * 4, &w_full[stage]);
-          if (PER_GROUP) {
-            bulk_g2s(sS2 + stage * S2_STAGE, p.s2_scales + (size_t)kb * p.N + sg.tile * BM, n_cnt, &w_full[stage]);
-            bulk_g2s(sS2 + stage * S2_STAGE + 128, p.s2_zeros + (size_t)kb * p.N + sg.tile * BM, n_cnt, &w_full[stage]);
+        for (int kb = sg.kb0; kb < sg.kb1; kb += KPS) {
+          const int cnt = min(KPS, sg.kb1 - kb);
+          mbar_wait(&w_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&w_full[stage], cnt * (W_KB + (PER_GROUP ? 2 * n_cnt : 0)));
+          for (int j = 0; j < cnt; ++j) {
+            tma_load_3d(sW + stage * C::W_STAGE + j * W_KB, &w_map, 0, (kb + j) * 4, sg.tile * 4, &w_full[stage]);
+            if (PER_GROUP) {
+              uint8_t* d = sS2 + stage * C::S2_STAGE + j * S2_KB;
+              bulk_g2s(d, p.s2_scales + (size_t)(kb + j) * p.N + sg.tile * BM, n_cnt, &w_full[stage]);
+              bulk_g2s(d + 128, p.s2_zeros + (size_t)(kb + j) * p.N + sg.tile * BM, n_cnt, &w_full[stage]);
+            }
           }
           if (++stage == C::W_STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      OB_T_DUMP(p.dbg_t[blockIdx.x * 32 + 0] = tw[0]);
     }
   } else if (warp == 1) {
     // ================================================================ activation producer (previous kernel's output)
@@ -189,155 +185,126 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       SegIter it; it.init(p);
       Seg sg;
       int stage = 0, phase = 0;
-      OB_T_DECL(1);
       while (it.next(sg)) {
-        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-          OB_T(0, mbar_wait(&ba_empty[stage], phase ^ 1));
-          mbar_arrive_expect_tx(&b_full[stage], OB_ABL(4) ? 0 : C::B_STAGE);
-          if (!OB_ABL(4)) tma_load_2d(sB + stage * C::B_STAGE, &act_map, kb * BK, 0, &b_full[stage]);
+        for (int kb = sg.kb0; kb < sg.kb1; kb += KPS) {
+          const int cnt = min(KPS, sg.kb1 - kb);
+          mbar_wait(&ba_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&b_full[stage], cnt * BN * BK);
+          for (int j = 0; j < cnt; ++j)
+            tma_load_2d(sB + stage * C::B_STAGE + j * BN * BK, &act_map, (kb + j) * BK, 0, &b_full[stage]);
           if (++stage == AB_STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      OB_T_DUMP(p.dbg_t[blockIdx.x * 32 + 1] = tw[0]);
     }
   } else if (warp == 2) {
-    // ================================================================ MMA issuer
+    // ================================================================ MMA issuer: one wait pair + one commit per step
     SegIter it; it.init(p);
     Seg sg;
     int st = 0, ph = 0, acc_phase = 0;
     constexpr uint32_t idesc = umma_idesc_i8(BM, BN, true, true);
     const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(sB));
     const uint32_t a_tmem0 = tmem_base + ACC_COLS;
-    OB_T_DECL(5);
-#ifdef OB_DEC_TIMING
-    const long long t_start = clock64();
-#endif
     while (it.next(sg)) {
-      OB_T(0, mbar_wait(acc_empty, acc_phase ^ 1));
+      mbar_wait(acc_empty, acc_phase ^ 1);
       tc_fence_after();
-      for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-        if (!OB_ABL(64)) OB_T(1, mbar_wait(&b_full[st], ph));
-        if (!OB_ABL(128)) OB_T(2, mbar_wait(&a_full[st], ph));
+      for (int kb = sg.kb0; kb < sg.kb1; kb += KPS) {
+        const int cnt = min(KPS, sg.kb1 - kb);
+        mbar_wait(&b_full[st], ph);
+        mbar_wait(&a_full[st], ph);
         tc_fence_after();
-#ifdef OB_DEC_TIMING
-        const long long t_i = clock64();
-#endif
         if (elect_one()) {
-          const uint64_t bdesc = bdesc0 + (uint64_t)((st * C::B_STAGE) >> 4);
-          const uint32_t a_tmem = a_tmem0 + st * A_COLS;
-          if (!OB_ABL(1)) {
+          uint64_t bdesc = bdesc0 + (uint64_t)((st * C::B_STAGE) >> 4);
+          uint32_t a_tmem = a_tmem0 + st * (A_COLS * KPS);
           umma_i8_ts(tmem_base, a_tmem, bdesc, idesc, kb > sg.kb0 ? 1u : 0u);
           umma_i8_ts(tmem_base, a_tmem + 8, bdesc + 2, idesc, 1u);
           umma_i8_ts(tmem_base, a_tmem + 16, bdesc + 4, idesc, 1u);
           umma_i8_ts(tmem_base, a_tmem + 24, bdesc + 6, idesc, 1u);
+          if (cnt > 1) {
+            bdesc += (uint64_t)((BN * BK) >> 4);
+            a_tmem += A_COLS;
+            umma_i8_ts(tmem_base, a_tmem, bdesc, idesc, 1u);
+            umma_i8_ts(tmem_base, a_tmem + 8, bdesc + 2, idesc, 1u);
+            umma_i8_ts(tmem_base, a_tmem + 16, bdesc + 4, idesc, 1u);
+            umma_i8_ts(tmem_base, a_tmem + 24, bdesc + 6, idesc, 1u);
           }
-#ifdef OB_DEC_TIMING
-          tw[3] += clock64() - t_i;
-#endif
-          if (OB_ABL(16)) {   // ablation: plain arrives instead of tcgen05.commit
-            mbar_arrive(&ba_empty[st]);
-            if (kb == sg.kb1 - 1) mbar_arrive(acc_full);
-          } else {
           umma_commit(&ba_empty[st]);
-          if (kb == sg.kb1 - 1) umma_commit(acc_full);
-          }
+          if (kb + cnt >= sg.kb1) umma_commit(acc_full);
         }
         __syncwarp();
-#ifdef OB_DEC_TIMING
-        tw[4] += clock64() - t_i;
-#endif
         if (++st == AB_STAGES) { st = 0; ph ^= 1; }
       }
       acc_phase ^= 1;
     }
-    OB_T_DUMP(if (lane == 0) { for (int i = 0; i < 5; ++i) p.dbg_t[blockIdx.x * 32 + 2 + i] = tw[i]; p.dbg_t[blockIdx.x * 32 + 7] = clock64() - t_start; });
   } else if (warp >= 4) {
-    // ================================================================ unpack (two sets alternating K-blocks) + epilogue
-    const int set = (warp - 4) >> 2;       // 0: even K-blocks of this CTA's sequence, 1: odd
+    // ================================================================ unpack (set j converts K-block j of every step) + epilogue
+    // Both sets take part in EVERY step (set 0: first K-block, set 1: second), so every ring is consumed strictly in
+    // order by the same waiters -- a parity wait is never more than one phase ahead -- and the two K-blocks of a step are
+    // converted concurrently.  A one-K-block step (odd tail of a segment) leaves set 1 with only the handshakes.
+    const int set = (warp - 4) >> 2;
     const int q = warp & 3;                // TMEM lane quarter == n32 block inside the tile
     const int et = threadIdx.x - 128;      // 0..255
     SegIter it; it.init(p);
     Seg sg;
     const uint32_t sW_u32 = smem_u32(sW), sS2_u32 = smem_u32(sS2);
     const uint32_t t_q = tmem_base + ((uint32_t)(q * 32) << 16);
-    int idx = 0;                           // running K-block index of this CTA (all segments)
+    int ws = 0, wph = 0, as = 0, aph = 0;
     int acc_phase = 0;
     bool waited = false;
-    OB_T_DECL(8);
+    static_assert(KPS == 2, "one unpack set per K-block of a step");
 
     while (it.next(sg)) {
-      // ---------------------------------------------------------------- unpack this set's K-blocks of the segment
-      for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++idx) {
-        if ((idx & 1) != set) continue;
-        const int ws = idx % C::W_STAGES, wph = (idx / C::W_STAGES) & 1;
-        const int as = idx % AB_STAGES, aph = (idx / AB_STAGES) & 1;
-        OB_T(0, mbar_wait(&w_full[ws], wph));
-#ifdef OB_DEC_TIMING
-        const long long t_a = clock64();
-#endif
+      for (int kb = sg.kb0; kb < sg.kb1; kb += KPS) {
+        const bool mine = kb + set < sg.kb1;
+        mbar_wait(&w_full[ws], wph);
         uint4 v[4];
-        const uint32_t wsm = sW_u32 + ws * W_STAGE + q * 2048 + lane * 16;
-        if (!OB_ABL(8)) {
+        uint32_t ps = 0, pz = 0;
+        if (mine) {
+          const uint32_t wsm = sW_u32 + ws * C::W_STAGE + set * W_KB + q * 2048 + lane * 16;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) v[a] = lds_v4(wsm + a * 512);
-        } else {
-#pragma unroll
-        for (int a = 0; a < 4; ++a) v[a] = make_uint4(idx, a, lane, 7);
-        }
-        uint32_t sc[4], zr[4];
-        if (PER_GROUP) {
-          const uint32_t ps = lds_u32(sS2_u32 + ws * S2_STAGE + q * 32 + (lane >> 2) * 4);
-          const uint32_t pz = lds_u32(sS2_u32 + ws * S2_STAGE + 128 + q * 32 + (lane >> 2) * 4);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sc[j] = (ps >> (8 * j)) & 0xFFu;
-            zr[j] = ((pz >> (8 * j)) & 0xFFu) * 0x01010101u;
+          for (int a = 0; a < 4; ++a) v[a] = lds_v4(wsm + a * 512);
+          if (PER_GROUP) {
+            ps = lds_u32(sS2_u32 + ws * C::S2_STAGE + set * S2_KB + q * 32 + (lane >> 2) * 4);
+            pz = lds_u32(sS2_u32 + ws * C::S2_STAGE + set * S2_KB + 128 + q * 32 + (lane >> 2) * 4);
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&w_empty[ws]);     // the packed stage is in registers: hand it back right away
-#ifdef OB_DEC_TIMING
-        tw[5] += clock64() - t_a;
-#endif
-        if (!OB_ABL(32)) OB_T(1, mbar_wait(&ba_empty[as], aph ^ 1));   // MMAs that read the slot's previous contents retired
+        if (lane == 0) mbar_arrive(&w_empty[ws]);     // this warp's part of the packed step is in registers
+        if (++ws == C::W_STAGES) { ws = 0; wph ^= 1; }
+        mbar_wait(&ba_empty[as], aph ^ 1);            // MMAs that read the slot's previous contents retired
         tc_fence_after();
-#ifdef OB_DEC_TIMING
-        const long long t_b = clock64();
-#endif
-        const uint32_t t_lo = t_q + ACC_COLS + as * A_COLS;
-        const uint32_t t_hi = t_lo + (16u << 16);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          uint32_t l0 = v[a].x & 0x0F0F0F0Fu, l1 = v[a].y & 0x0F0F0F0Fu, l2 = v[a].z & 0x0F0F0F0Fu, l3 = v[a].w & 0x0F0F0F0Fu;
-          uint32_t h0 = (v[a].x >> 4) & 0x0F0F0F0Fu, h1 = (v[a].y >> 4) & 0x0F0F0F0Fu, h2 = (v[a].z >> 4) & 0x0F0F0F0Fu,
-                   h3 = (v[a].w >> 4) & 0x0F0F0F0Fu;
+        if (mine) {
+          uint32_t sc[4], zr[4];
           if (PER_GROUP) {
-            // rows: l0,l2 -> c (scale 0); l1,l3 -> c+8 (scale 1); h0,h2 -> c+16 (scale 2); h1,h3 -> c+24 (scale 3)
-            l0 = vadd4(l0 * sc[0], zr[0]); l2 = vadd4(l2 * sc[0], zr[0]);
-            l1 = vadd4(l1 * sc[1], zr[1]); l3 = vadd4(l3 * sc[1], zr[1]);
-            h0 = vadd4(h0 * sc[2], zr[2]); h2 = vadd4(h2 * sc[2], zr[2]);
-            h1 = vadd4(h1 * sc[3], zr[3]); h3 = vadd4(h3 * sc[3], zr[3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              sc[i] = (ps >> (8 * i)) & 0xFFu;
+              zr[i] = ((pz >> (8 * i)) & 0xFFu) * 0x01010101u;
+            }
           }
-          if (!OB_ABL(2)) {
-          tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
-          tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
-          } else if (l0 + h3 == 0x12345u) {
+          const uint32_t t_lo = t_q + ACC_COLS + (as * KPS + set) * A_COLS;
+          const uint32_t t_hi = t_lo + (16u << 16);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const uint4 w = v[a];
+            uint32_t l0 = w.x & 0x0F0F0F0Fu, l1 = w.y & 0x0F0F0F0Fu, l2 = w.z & 0x0F0F0F0Fu, l3 = w.w & 0x0F0F0F0Fu;
+            uint32_t h0 = (w.x >> 4) & 0x0F0F0F0Fu, h1 = (w.y >> 4) & 0x0F0F0F0Fu, h2 = (w.z >> 4) & 0x0F0F0F0Fu,
+                     h3 = (w.w >> 4) & 0x0F0F0F0Fu;
+            if (PER_GROUP) {
+              // rows: l0,l2 -> c (scale 0); l1,l3 -> c+8 (scale 1); h0,h2 -> c+16 (scale 2); h1,h3 -> c+24 (scale 3)
+              l0 = vadd4(l0 * sc[0], zr[0]); l2 = vadd4(l2 * sc[0], zr[0]);
+              l1 = vadd4(l1 * sc[1], zr[1]); l3 = vadd4(l3 * sc[1], zr[1]);
+              h0 = vadd4(h0 * sc[2], zr[2]); h2 = vadd4(h2 * sc[2], zr[2]);
+              h1 = vadd4(h1 * sc[3], zr[3]); h3 = vadd4(h3 * sc[3], zr[3]);
+            }
             tmem_st_16x128b_x2(t_lo + a * 8, l0, l1, l2, l3);
+            tmem_st_16x128b_x2(t_hi + a * 8, h0, h1, h2, h3);
           }
+          tmem_st_wait();
         }
-#ifdef OB_DEC_TIMING
-        tw[6] += clock64() - t_b;
-#endif
-        OB_T(2, tmem_st_wait());   // the other set is converting the next K-block meanwhile
-#ifdef OB_DEC_TIMING
-        const long long t_c = clock64();
-#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[as]);
-#ifdef OB_DEC_TIMING
-        tw[7] += clock64() - t_c;
-#endif
+        if (++as == AB_STAGES) { as = 0; aph ^= 1; }
       }
 
       // ---------------------------------------------------------------- epilogue of the segment (all eight warps)
@@ -360,12 +327,9 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
         sTok[et] = (et < p.M) ? __half2float(p.ascales[et]) : 0.f;
         sTok[BN + et] = (!PER_GROUP && et < p.M) ? __half2float(p.a_ssums[et]) : 0.f;
       }
-      OB_T(3, mbar_wait(acc_full, acc_phase));
+      mbar_wait(acc_full, acc_phase);
       if (warp == 4) OB_GT(28);     // accumulator of the (last) segment complete
       acc_phase ^= 1;
-#ifdef OB_DEC_TIMING
-      const long long t_epi0 = clock64();
-#endif
       tc_fence_after();
       bar_epi();   // sTok visible
       constexpr int HALF = BN / 2;                       // tokens per set
@@ -439,11 +403,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       }
       bar_epi();   // sTok / sFlag free for the next segment
       if (warp == 4) OB_GT(29);     // epilogue (incl. finalisation) of the (last) segment done
-#ifdef OB_DEC_TIMING
-      tw[4] += clock64() - t_epi0;
-#endif
     }
-    OB_T_DUMP(if (lane == 0 && q == 0) { for (int i = 0; i < 8; ++i) p.dbg_t[blockIdx.x * 32 + 8 + set * 8 + i] = tw[i]; });
   }
 
   tc_fence_before();
@@ -468,21 +428,31 @@ static int launch(const CUtensorMap& amap, const CUtensorMap& wmap, const Params
 
 }  // namespace dec
 
-// Scheduling: every CTA gets `upc` consecutive (tile, K-block) units.  A CTA whose range stays inside one tile runs one
-// epilogue, one that crosses a tile boundary runs two (or more), and a split tile costs a finalisation, so ranges aligned
-// to the tiles are preferred when they cost little parallelism:  cost(upc) = upc * T_KB + segments(upc) * T_EPI.
-static int choose_upc(int n_tiles, int KB, int max_ctas) {
+// Scheduling: every CTA gets `upc` consecutive (tile, K-block) units.  Cost model in us, fitted to the sweep of every
+// choice on B200 (profiles/r2_upc_sweep.log; the ~3.5 us launch floor is common to all and left out):
+//   * an SM moves one K-block per ~0.2 us however many CTAs share it: streaming = (CTAs per SM) x upc x 0.2;
+//   * a tile that is not split ends with a ~0.3 us epilogue (direct fp16 stores);
+//   * ANY split costs ~5 us (reds, fence, arrival counter, read-back and finalisation by the last contributor), plus
+//     ~0.01 us per contributing CTA of L2 atomic traffic -- so a whole 32-K-block tile per CTA (6.4 us) beats an 8-way
+//     split of it, and splitting only pays for long K (down_proj) or very few tiles;
+//   * ranges that straddle tile boundaries add a second epilogue and an uneven finish (~3 us).
+static int choose_upc(int n_tiles, int KB, int sms, int ctas_per_sm, int BN) {
+  (void)BN;
   const long long units = (long long)n_tiles * KB;
+  const int max_ctas = sms * ctas_per_sm;
   const int lo = (int)((units + max_ctas - 1) / max_ctas);
-  const float T_KB = 0.20f, T_EPI = 0.9f;
-  int best = lo;
+  if (lo >= KB) return KB * ((lo + KB - 1) / KB);   // at least a tile per CTA: whole tiles, no split
+  const float T_KB = 0.2f, T_FULL = 0.3f, T_SPLIT = 5.0f, T_CTA = 0.01f, T_UNALIGNED = 3.0f;
+  int best = KB;
   float best_cost = 1e30f;
-  for (int upc = lo; upc <= KB && upc <= 2 * lo + 4; ++upc) {
-    const int segs = (KB % upc == 0) ? 1 : ((upc < KB) ? 2 : 1 + (upc + KB - 1) / KB);
-    const float cost = upc * T_KB + segs * T_EPI + ((KB % upc == 0 && upc == KB) ? -0.5f * T_EPI : 0.f);
+  for (int upc = lo; upc <= KB; ++upc) {
+    const long long n_ctas = (units + upc - 1) / upc;
+    const int per_sm = (int)((n_ctas + sms - 1) / sms);
+    float cost = per_sm * upc * T_KB;
+    cost += (upc < KB) ? (T_SPLIT + n_ctas * T_CTA) : T_FULL;
+    if (KB % upc) cost += T_UNALIGNED;
     if (cost < best_cost - 1e-6f) { best_cost = cost; best = upc; }
   }
-  if (lo > KB) return lo;   // more than a tile per CTA: plain stream-K
   return best;
 }
 
@@ -513,14 +483,12 @@ int w4a8_gemm_decode_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st)
     static int launch_idx = 0;
     const char* e = getenv("OB_DEC_DBGT");
     p.dbg_t = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) + (size_t)(launch_idx++ % 64) * 1024 * 32 : nullptr;
-    const char* a2 = getenv("OB_DEC_DBG");
-    p.dbg = a2 ? atoi(a2) : 0;
   }
 #endif
   static const int ctas_per_sm = [] { const char* e = getenv("OB_GEMM_DEC_CTAS_PER_SM"); return e ? std::max(1, std::min(2, atoi(e))) : 2; }();
   int max_ctas = a.force_ctas > 0 ? std::min(a.force_ctas, 2 * sms) : ctas_per_sm * sms;
   const long long units = (long long)p.n_tiles * p.kb_per_tile;
-  p.units_per_cta = a.force_ctas > 0 ? (int)((units + max_ctas - 1) / max_ctas) : choose_upc(p.n_tiles, p.kb_per_tile, max_ctas);
+  p.units_per_cta = a.force_ctas > 0 ? (int)((units + max_ctas - 1) / max_ctas) : choose_upc(p.n_tiles, p.kb_per_tile, sms, ctas_per_sm, BN);
   const int grid = (int)((units + p.units_per_cta - 1) / p.units_per_cta);
   CUtensorMap amap, wmap;
   if (int e = make_act_map(&amap, a.in_feats, a.M, a.K, BN)) return e;

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-role wait cycles of the decode GEMM (w4a8_gemm_decode.cu).  Needs the instrumented build:
+"""Globaltimer timeline of PDL-chained decode GEMM launches (w4a8_gemm_decode.cu).  Needs the instrumented build:
 
     OB_DEC_TIMING=1 python -m omniserve_b200.build --force && python tools/dec_waits.py ; python -m omniserve_b200.build --force
 """
@@ -18,42 +18,6 @@ from omniserve_b200 import _lib as L  # noqa: E402
 U = ["wait w_full", "wait ba_empty", "wait::st", "wait acc_full", "epilogue", "lds + arrive w_empty", "convert + tcgen05.st issue",
      "fence + arrive a_full"]
 launches = 0
-NAMES = ["Wprod wait w_empty", "Bprod wait ba_empty", "MMA wait acc_empty", "MMA wait b_full", "MMA wait a_full",
-         "MMA issue 4 x umma (elected lane)", "MMA issue + commit + syncwarp", "MMA total"] + [f"U0 {x}" for x in U] + [f"U1 {x}" for x in U]
-
-
-def run(M, N, K, ctas, tag):
-    w = torch.randint(-128, 128, (N, K // 2), dtype=torch.int8, device=dev)
-    x = torch.randint(-127, 128, (M, K), dtype=torch.int8, device=dev)
-    s1 = torch.full((N,), 0.01, dtype=torch.float16, device=dev)
-    sz = torch.full((N,), 0.08, dtype=torch.float16, device=dev)
-    sa = torch.full((M,), 0.02, dtype=torch.float16, device=dev)
-    ss = torch.full((M,), 0.1, dtype=torch.float16, device=dev)
-    out = torch.empty((M, N), dtype=torch.float16, device=dev)
-    global launches
-    for _ in range(3):
-        dbg.zero_()
-        c = L.lib().ob_w4a8_gemm_ex(0, L.ptr(x), L.ptr(w), 0, 0, L.ptr(s1), L.ptr(sa), L.ptr(sz), L.ptr(ss), L.ptr(out), M, N, K, N, 0,
-                                    3, ctas, L.stream())
-        assert c == 0
-        torch.cuda.synchronize()
-        blk = launches % 64
-        launches += 1
-    d = dbg[blk].cpu().float()
-    used = d[:, 7] > 0
-    n = int(used.sum())
-    kb = (N // 128) * (K // 128) / max(n, 1)
-    m = d[used].mean(0)
-    print(f"== {tag}: M={M} N={N} K={K} grid={n} ({kb:.1f} K-blocks per CTA); cycles per CTA (mean), per K-block in ()")
-    for i, nm in enumerate(NAMES):
-        print(f"   {nm:36s} {m[i]:10.0f}  ({m[i] / kb:7.1f})")
-
-
-run(64, 18944, 14336, 148, "148 x 112 kb")
-run(64, 4096, 14336, 32, "32 CTAs x 112 kb")
-run(64, 28672, 4096, 0, "gate_up auto")
-run(64, 4096, 4096, 0, "o_proj auto")
-run(16, 4096, 14336, 32, "M=16 32 CTAs x 112 kb")
 
 
 def timeline(shapes, M=64, layers=3, tag=""):

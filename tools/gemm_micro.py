@@ -83,6 +83,25 @@ def chain(M, shapes, mode, ctas, layers=8, tag=""):
     print(f"{tag:34s} M={M:3d} mode={mode:2d} ctas={ctas:3d}: {us:8.2f} us per layer (4 GEMMs)  {by / us / 1e3:8.1f} GB/s", flush=True)
 
 
+if __name__ == "__main__" and os.environ.get("OB_UPC_SWEEP"):
+    # decode kernel: time every "units per CTA" choice (through force_ctas) for the shapes that matter
+    SH = {"qkv": (6144, 4096), "o": (4096, 4096), "gate_up": (28672, 4096), "down": (4096, 14336),
+          "tp8 qkv": (768, 4096), "tp8 o": (4096, 512), "tp8 gate_up": (3584, 4096), "tp8 down": (4096, 1792),
+          "tp2 qkv": (3072, 4096), "tp2 o": (4096, 2048), "tp2 gate_up": (14336, 4096), "tp2 down": (4096, 7168)}
+    for nm, (N, K) in SH.items():
+        tiles, KB = N // 128, K // 128
+        units = tiles * KB
+        seen = set()
+        for upc in sorted(set([max(1, (units + 295) // 296), 1, 2, 4, 7, 8, 14, 16, 25, 28, 32, 56, KB])):
+            if upc > KB or upc < (units + 295) // 296:
+                continue
+            ctas = (units + upc - 1) // upc
+            if ctas in seen or ctas > 296:
+                continue
+            seen.add(ctas)
+            run(64, N, K, mode=3, ctas=ctas, tag=f"{nm} upc={upc}")
+    sys.exit(0)
+
 if __name__ == "__main__" and os.environ.get("OB_DEC_EXP"):
     LL = [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)]
     names = ["qkv", "o_proj", "gate_up", "down"]
