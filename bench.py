@@ -263,7 +263,22 @@ def prefill_gemm_tops(model, M=8192):
 
 # DRAM traffic per roofline unit from one `ncu --set full` capture per kernel (tools/ncu_targets.py, round 1):
 # the four decode GEMM launches of a layer: qkv 14.52 + o 9.79 + gate_up 59.48 + down 31.42 MB; attention 90.02 + 2.84 MB.
-NCU_DRAM_BYTES = {"w4a8_gemm(decode,4 launches/layer)": 115.2e6, "kv4_decode_attention": 92.9e6}
+NCU_DRAM_BYTES = {"w4a8_gemm(decode,4 launches/layer)": 115.2e6, "kv4_decode_attention": 92.9e6}   # round-1 captures (fallback)
+
+
+def ncu_traffic():
+    """DRAM bytes per roofline unit from the newest committed `ncu --set full` capture (tools/ncu_targets.py ->
+    tools/ncu_summary.py -> profiles/r<N>_ncu/traffic.json)."""
+    for rnd in ("r2", "r1"):
+        f = os.path.join(ROOT, "profiles", f"{rnd}_ncu", "traffic.json")
+        if os.path.exists(f):
+            try:
+                d = json.load(open(f))
+                if d.get("per_layer_dram_bytes"):
+                    return d["per_layer_dram_bytes"], f"profiles/{rnd}_ncu/traffic.json ({d.get('source', '')})"
+            except Exception:
+                pass
+    return NCU_DRAM_BYTES, "constants recorded from the round-1 captures (profiles/r1_ncu/*.raw.csv)"
 INT8_PEAK_RECORDED = 4350.0  # TOPS, tools/umma_rate.cu on this pool's B200 (profiles/r1_umma_rate.log): 8188 MAC/clk/SM
 
 
@@ -282,29 +297,33 @@ def int8_peak():
     return INT8_PEAK_RECORDED, "recorded (profiles/r1_umma_rate.log)"
 
 
-def measure_tp(cfg, dev, rank, world, steps, warmup):
-    """Tensor-parallel decode (column/row sharded W4A8 layers, one NCCL all-reduce after o_proj and after down_proj,
-    captured in the CUDA graph): same global batch of 64 over all GPUs (strong scaling)."""
+def measure_secondary(cfg, dev, rank, world, steps, warmup, tp, batch=BATCH, tag=None):
+    """A second decode measurement next to the headline: tp == world -> tensor parallel (column/row sharded W4A8 layers, one
+    exchange after o_proj and after down_proj; same global batch, strong scaling), tp == 1 -> one replica per GPU
+    (weak scaling, no data-path collective).  Same protocol as the headline (real prefill, graph replay, max over ranks)."""
     import torch.distributed as dist
     from omniserve_b200.model import DecodeGraph, LlamaW4A8
-    model = LlamaW4A8(cfg, dev, rank, world)
+    model = LlamaW4A8(cfg, dev, rank if tp > 1 else 0, tp, seed=0 if tp > 1 else rank)
+    BATCH_ = batch
     max_ctx = PROMPT_LEN + GEN_LEN
-    model.alloc(BATCH, max_ctx, PREFILL_SUB_BATCH * PROMPT_LEN)
+    sub = min(PREFILL_SUB_BATCH, BATCH_)
+    model.alloc(BATCH_, max_ctx, sub * PROMPT_LEN)
     g = torch.Generator().manual_seed(42)
-    prompts = torch.randint(0, cfg.vocab_size, (BATCH, PROMPT_LEN), generator=g)
+    prompts = torch.randint(0, cfg.vocab_size, (BATCH_, PROMPT_LEN), generator=g)
     first, chunk_ms = [], []
-    for s0 in range(0, BATCH, PREFILL_SUB_BATCH):
-        toks = prompts[s0:s0 + PREFILL_SUB_BATCH].reshape(-1).to(dev)
+    for s0 in range(0, BATCH_, sub):
+        toks = prompts[s0:s0 + sub].reshape(-1).to(dev)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
-        first.append(model.prefill(toks, [PROMPT_LEN] * PREFILL_SUB_BATCH, seq_offset=s0))
+        first.append(model.prefill(toks, [PROMPT_LEN] * sub, seq_offset=s0))
         c1.record()
         chunk_ms.append((c0, c1))
     torch.cuda.synchronize()
     per_chunk = sorted(x.elapsed_time(y) for x, y in chunk_ms)
-    prefill_ms = sum(per_chunk[:-1]) * len(per_chunk) / max(1, len(per_chunk) - 1)
-    collective = "NCCL all-reduce (fp16 sum, [64, 4096]) after o_proj and after down_proj, inside the CUDA graph"
-    if os.environ.get("OB_PEER_ALLREDUCE", "1") != "0":
+    prefill_ms = (sum(per_chunk[:-1]) * len(per_chunk) / max(1, len(per_chunk) - 1)) if len(per_chunk) > 1 else per_chunk[0]
+    collective = "none (independent replicas)" if tp == 1 else \
+        "NCCL all-reduce (fp16 sum, [batch, hidden]) after o_proj and after down_proj, inside the CUDA graph"
+    if tp > 1 and os.environ.get("OB_PEER_ALLREDUCE", "1") != "0":
         try:   # all-reduce fused into the following add+norm+quant kernel over NVLink peer memory
             model.enable_peer_allreduce()
             collective = ("all-reduce fused into the add+norm+quant kernel that consumes it: partial sums read from NVLink "
@@ -327,9 +346,11 @@ def measure_tp(cfg, dev, rank, world, steps, warmup):
     ms = float(tms.item())
     del graph, model
     torch.cuda.empty_cache()
-    return {"value": BATCH * steps / (ms / 1e3), "unit": "tok/s", "ms_per_step": ms / steps, "steps": steps,
-            "parallelism": f"tp{world}", "scaling": "strong", "global_batch": BATCH,
-            "prefill_tok_per_s": BATCH * PROMPT_LEN / (prefill_ms / 1e3),
+    reps = world if tp == 1 else 1
+    return {"value": BATCH_ * reps * steps / (ms / 1e3), "unit": "tok/s", "ms_per_step": ms / steps, "steps": steps,
+            "parallelism": f"tp{world}" if tp > 1 else f"dp{world}", "scaling": "strong" if tp > 1 else "weak",
+            "global_batch": BATCH_ * reps, "model": tag or "Llama-3-8B",
+            "prefill_tok_per_s": BATCH_ * reps * PROMPT_LEN / (prefill_ms / 1e3),
             "collective": collective}
 
 
@@ -342,9 +363,10 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (result is then marked invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parallelism", default="auto", choices=["auto", "dp", "tp"],
-                    help="N > 1: dp = one bs=64 replica per GPU (weak scaling, no data-path collective; what an 8B "
-                         "model is served with), tp = tensor parallel over all GPUs (strong scaling, NCCL all-reduce "
-                         "after o_proj and down_proj).  auto = dp, with the tp measurement added under \"tp\".")
+                    help="N > 1: tp = tensor parallel over all GPUs (BASELINE north star: head / column sharding, one "
+                         "exchange after o_proj and after down_proj; same global batch of 64 -> strong scaling), dp = one "
+                         "bs=64 replica per GPU (weak scaling, no data-path collective).  auto = tp as the headline, with the "
+                         "dp measurement added under \"dp\".")
     a = ap.parse_args()
     # Keep stdout clean for the ONE JSON line: libraries (NCCL banner, warnings) print to fd 1 in worker processes.
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -362,7 +384,7 @@ def main():
     if use_dist:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    mode = "dp" if a.parallelism in ("auto", "dp") else "tp"
+    mode = "tp" if a.parallelism in ("auto", "tp") else "dp"
     tp = world if (use_dist and mode == "tp") else 1
     replicas = world if (use_dist and mode == "dp") else 1
 
@@ -429,7 +451,18 @@ def main():
     pinned_out = torch.zeros((BATCH,), dtype=torch.int64).pin_memory()
     pinned_in.copy_(first.cpu())
 
+    collective = None
     if a.impl == "ours":
+        if tp > 1:
+            collective = "NCCL all-reduce (fp16 sum, [64, 4096]) after o_proj and after down_proj, inside the CUDA graph"
+            if os.environ.get("OB_PEER_ALLREDUCE", "1") != "0":
+                try:   # all-reduce fused into the following add+norm+quant kernel over NVLink peer memory
+                    model.enable_peer_allreduce()
+                    collective = ("all-reduce fused into the add+norm+quant kernel that consumes it: every rank's row-parallel "
+                                  "partial sums are read straight from NVLink peer (symmetric) memory, per-block epoch flags, "
+                                  "no NCCL call in the decode layers")
+                except Exception as e:  # symmetric memory unavailable: keep NCCL
+                    print("peer all-reduce unavailable, using NCCL:", repr(e)[:200], file=sys.stderr)
         graph = DecodeGraph(model, max_ctx)
         graph.tokens.copy_(first)
 
@@ -510,8 +543,8 @@ def main():
     }
     dom = "w4a8_gemm(decode,4 launches/layer)" if gemm_ms >= kt["attention"] else "kv4_decode_attention"
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-            "frac": kernels[dom]["frac_hbm"], "traffic": NCU_DRAM_BYTES.get(dom), "peak_source": peak_src,
-            "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, cold launches (profiles/r1_ncu/*.raw.csv)",
+            "frac": kernels[dom]["frac_hbm"], "traffic": (ncu_traffic()[0].get(dom) if tp == 1 else None), "peak_source": peak_src,
+            "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, cold launches: " + ncu_traffic()[1],
             "share_of_step": cfg.num_hidden_layers * kernels[dom]["ms_per_layer"] / (ms / a.steps)}
     prefill = None
     if a.impl == "ours" and tp == 1 and not skip_prefill:
@@ -524,20 +557,22 @@ def main():
 
     step_floor_ms = (model.weight_bytes() + model.lm_head.numel() * 2
                      + BATCH * mid_ctx * model.hkv * 136 * cfg.num_hidden_layers) / hbm_peak / 1e6
-    want_tp = use_dist and mode == "dp" and a.parallelism == "auto" and os.environ.get("OB_BENCH_TP", "1") != "0"
-    if rank != 0 and not want_tp:
+    want_dp = use_dist and mode == "tp" and a.parallelism == "auto" and os.environ.get("OB_BENCH_DP", "1") != "0"
+    want_c4 = use_dist and mode == "tp" and world == 8 and os.environ.get("OB_BENCH_C4", "1") != "0"
+    if rank != 0 and not (want_dp or want_c4):
         return 0
     line = {
         "metric": "decode tok/s Llama-3-8B W4A8KV4 bs=64",
         "value": value, "unit": "tok/s", "n_gpus": world if use_dist else 1, "steps": a.steps, "warmup": max(3, a.warmup),
-        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak" if mode == "dp" else "strong",
+        "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": ("weak" if mode == "dp" else "strong") if use_dist else "weak",
         "vs_baseline": None,
         "dtype": "int8 (W4A8, s32 accumulate) + fp16 KV4 attention", "data": "synthetic (random-init weights, random prompts)",
         "config": {"workload": "Llama-3-8B W4A8KV4 per-channel, qserve_benchmark.py semantics bs=64 in=1024 out=512: "
                                "decode steps after a real 64x1024 prefill", "global_batch": BATCH * replicas, "prompt_len": PROMPT_LEN,
                    "ctx_at_first_timed_step": ctx_start,
                    "parallelism": (f"dp{replicas} (one bs={BATCH} replica per GPU, no data-path collective)" if replicas > 1
-                                   else f"tp{tp}"), "cuda_graph": a.impl == "ours",
+                                   else f"tp{tp}"), "collective": collective, "cuda_graph": a.impl == "ours",
                    "l2": "per-step working set (3.5 GB W4 weights + 2.8 GB KV4 + 1 GB lm_head) >> 126 MB L2; no flush needed",
                    "layers": cfg.num_hidden_layers},
         "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": BATCH * replicas * 8,
@@ -562,22 +597,32 @@ def main():
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
 
-    if want_tp:
-        # Secondary measurement: the same global batch of 64 tensor-parallel over all GPUs.  It must never take the
-        # headline down: exceptions are recorded, and a watchdog prints the line and ends the process if it hangs.
+    if want_dp or want_c4:
+        # Secondary measurements.  They must never take the headline down: exceptions are recorded, and a watchdog prints
+        # the line and ends the process if one hangs.
         done = threading.Event()
 
         def watchdog():
-            if not done.wait(timeout=float(os.environ.get("OB_BENCH_TP_TIMEOUT", "300"))):
+            if not done.wait(timeout=float(os.environ.get("OB_BENCH_SECONDARY_TIMEOUT", "420"))):
                 if rank == 0:
-                    line["tp"] = {"error": "tensor-parallel sub-measurement timed out"}
+                    line.setdefault("dp", {"error": "secondary measurement timed out"})
                     emit()
                 os._exit(0)
         threading.Thread(target=watchdog, daemon=True).start()
-        try:
-            line["tp"] = measure_tp(cfg, dev, rank, world, min(a.steps, 64), a.warmup)
-        except Exception as e:
-            line["tp"] = {"error": repr(e)[:300]}
+        del graph, model
+        torch.cuda.empty_cache()
+        if want_dp:   # one bs=64 replica per GPU, no data-path collective (how an 8B model is usually served)
+            try:
+                line["dp"] = measure_secondary(cfg, dev, rank, world, min(a.steps, 64), a.warmup, tp=1)
+            except Exception as e:
+                line["dp"] = {"error": repr(e)[:300]}
+        if want_c4:   # BASELINE config 4: Llama-3-70B W4A8KV4, tensor-parallel 8, bs = 16
+            try:
+                c70 = LlamaConfig.llama3_70b()
+                line["c4"] = measure_secondary(c70, dev, rank, world, min(a.steps, 32), a.warmup, tp=world, batch=16,
+                                               tag="Llama-3-70B (BASELINE config 4: TP=8, bs=16, in=1024)")
+            except Exception as e:
+                line["c4"] = {"error": repr(e)[:300]}
         done.set()
     if rank != 0:
         return 0

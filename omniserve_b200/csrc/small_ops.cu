@@ -75,12 +75,17 @@ struct NoPeer {};   // kernel-parameter placeholder of the non-TP instantiations
 template <bool PEER> struct PeerSel { using type = NoPeer; };
 template <> struct PeerSel<true> { using type = PeerCtx; };
 
-OB_DEVICE void st_release_sys_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// Flag traffic of the exchange barrier.  The partial sums a flag announces were written by the PREVIOUS kernel (the
+// row-parallel GEMM), whose completion -- awaited with griddepcontrol.wait before the flag is sent -- already made them
+// visible in this GPU's L2, which is where peers read them over NVLink; so the flag itself is a relaxed system-scope store
+// and the wait a relaxed system-scope poll followed by ONE acquire fence (a release / acquire pair per poll iteration
+// cost ~6 us per exchange at tp2, profiles/r2_tp_step.md).
+OB_DEVICE void st_flag_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-OB_DEVICE uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+OB_DEVICE uint32_t ld_flag_sys_u32(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 OB_DEVICE uint4 ld_peer_v4(const void* p) {   // peer memory is not coherent with this SM's L1: bypass it
@@ -100,9 +105,10 @@ OB_DEVICE void peer_barrier(const PeerCtx& c, uint32_t* e_s) {
   const uint32_t e = *e_s;
   if ((int)threadIdx.x < c.world) {
     const int p = threadIdx.x;
-    st_release_sys_u32(c.flags[p] + blockIdx.x * 8 + c.rank, e);
-    while ((int)(ld_acquire_sys_u32(c.flags[c.rank] + blockIdx.x * 8 + p) - e) < 0) {
+    st_flag_sys_u32(c.flags[p] + blockIdx.x * 8 + c.rank, e);
+    while ((int)(ld_flag_sys_u32(c.flags[c.rank] + blockIdx.x * 8 + p) - e) < 0) {
     }
+    asm volatile("fence.acquire.sys;" ::: "memory");
   }
   __syncthreads();
 }
@@ -119,6 +125,50 @@ OB_DEVICE uint4 peer_sum_v8(const PeerCtx& c, size_t row, int H, int idx) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) r.h[j] = __float2half_rn(acc[j]);
   return r.u;
+}
+
+// All of this thread's vectors of the row at once: the loads of up to four peers x NV vectors are issued back to back
+// before anything depends on them, so a row costs ceil(W / 4) NVLink round trips instead of NV x W dependent ones
+// (round 2: the one-vector-at-a-time loop made the fused exchange 18 us at tp2, profiles/r2_tp_step.md).  Same fp32
+// summation order (rank 0..W-1) and single fp16 rounding as peer_sum_v8.
+template <int NV>
+OB_DEVICE void peer_sum_row(const PeerCtx& c, size_t row, int H, int nvec, V8 (&out)[NV]) {
+  float acc[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int p0 = 0; p0 < c.world; p0 += 4) {
+    V8 x[4][NV];
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+      if (p0 + pp < c.world) {
+        const uint4* base = reinterpret_cast<const uint4*>(c.bufs[p0 + pp] + row * H);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int idx = threadIdx.x + i * blockDim.x;
+          if (idx < nvec) x[pp][i].u = ld_peer_v4(base + idx);
+        }
+      }
+    }
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+      if (p0 + pp < c.world) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int idx = threadIdx.x + i * blockDim.x;
+          if (idx < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] += __half2float(x[pp][i].h[j]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[i].h[j] = __float2half_rn(acc[i][j]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -187,7 +237,11 @@ __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __rest
   V8 v[MAXV];
   float s1 = 0.f, s2 = 0.f;
   pdl_wait();
-  if constexpr (PEER) peer_barrier(pc, &epoch_s);
+  [[maybe_unused]] V8 psum[PEER ? 4 : 1];
+  if constexpr (PEER) {
+    peer_barrier(pc, &epoch_s);
+    peer_sum_row<4>(pc, row, H, nvec, psum);   // rows of <= 4096 halves (4 vectors per thread at 128 threads)
+  }
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
@@ -195,7 +249,7 @@ __global__ void __launch_bounds__(128) rmsnorm_quant_kernel(const __half* __rest
       v[i].u = ld_nc_v4(src + idx);
       if (ADD) {
         V8 dl;
-        if constexpr (PEER) dl.u = peer_sum_v8(pc, row, H, idx);
+        if constexpr (PEER) dl.u = (i < 4) ? psum[i < 4 ? i : 0].u : peer_sum_v8(pc, row, H, idx);
         else dl.u = ld_nc_v4(reinterpret_cast<const uint4*>(delta + row * H) + idx);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[i].h2[j] = __hadd2(v[i].h2[j], dl.h2[j]);
