@@ -42,6 +42,17 @@ int ob_w4a8_gemm_per_group(const int8_t* in_feats, const int8_t* kernel, const i
                            const int8_t* scales_i8, const void* wscales, const void* ascales, void* out_feats,
                            int M, int N, int K, int ldc, void* stream);
 
+/* ---- grouped W4A8 per-channel GEMM for mixture-of-experts layers.  Interface of the reference's UNRELEASED op
+ * `moe_gemm_forward_cuda_api(x, qweight, s1_scales, input_scales, s1_szeros, input_sum, problem_sizes)`
+ * (omniserve/modeling/layers/quantized_linear/w4a8_moe_linear.py:83-94, buffers :30-72): in_feats int8 [T, K] with token
+ * rows sorted by expert; kernel int8 [E, N, K/2], each expert in the w4a8_linear.py:297-327 tile layout; wscales / w_szs
+ * fp16 [E, N]; ascales / a_ssums fp16 [T]; problem_sizes_host[e] = rows routed to expert e (HOST array, sum == T);
+ * out fp16 [T, ldc] = per row r of expert e: (in[r] . W_e^T) * wscales[e,n] * ascales[r] - w_szs[e,n] * a_ssums[r].
+ * N % 128 == 0, K % 128 == 0. */
+int ob_w4a8_moe_gemm(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales,
+                     const void* w_szs, const void* a_ssums, void* out_feats, const int* problem_sizes_host, int num_experts,
+                     int T, int N, int K, int ldc, void* stream);
+
 /* ---- qgemm_w8a8.w8a8_gemm_forward_cuda (kernels/csrc/qgemm/w8a8/w8a8_gemm_cuda.cu:537-600, epilogue :515-530)
  * out[M, ldc] (fp16) = (in[M,K] int8 . kernel[N,K]^T int8, s32 accumulate) * (wscales[n] * ascales[m]); kernel is plain
  * row-major [N, K] (w8a8_linear.py:42-52).  N % 8 == 0, K % 128 == 0. */
@@ -168,6 +179,12 @@ typedef struct ob_kv4_prefill_args {
   int rotary_embedding_dim; float rotary_base; float rotary_scale;
 } ob_kv4_prefill_args;
 int ob_kv4_apply_rope_update_kv_cache(const ob_kv4_prefill_args* args, void* stream);
+/* Extension: the call above FUSED with fused_attention_ctx_pool.paged_min_max_pool of the
+ * rotated keys (ctx_update_kv.py:104-178 runs the two back to back): one pass rotates q / k in place, writes the KV4 pages
+ * and the kmax / kmin statistics of every `tokens_per_sub_chunk`-token sub-chunk of the retrieval heads (statistics row of a
+ * head = head_rank_table[head]).  Page bytes and statistics are bit-identical to the two-op chain.  tokens_per_sub_chunk
+ * must be 16, num_retrieval_kv_heads <= 8. */
+int ob_kv4_apply_rope_update_kv_cache_pool(const ob_kv4_prefill_args* args, int tokens_per_sub_chunk, void* stream);
 
 /* ---- compute_padding_offsets (common/input_metadata_helper.cu:16-49) */
 int ob_compute_padding_offsets(int32_t* out, const int32_t* cu_seqlens, int batch, int max_seqlen, void* stream);
@@ -200,6 +217,15 @@ typedef struct ob_page_selector_args {
   int tokens_per_sub_chunk, hidden_dim_per_retrieval_token;
 } ob_page_selector_args;
 int ob_kv4_page_selector(const ob_page_selector_args* args, void* stream);
+
+/* Extension: the page choice the reference makes with torch ops after the selector
+ * (omniserve/modeling/layers/decoding_attention.py:132-141: view [B,Hq,pages,4] -> max -> topk(k-1) over all but the newest
+ * page -> cat newest -> int32) as one kernel.  scores: the selector output, fp16 [rows = B*Hq, pitch] sub-chunk scores;
+ * out int32 [rows, k_out]: the k_out-1 best of pages 0..total_pages-2 (ties at the threshold broken by page order; torch's
+ * tie order is unspecified), then page total_pages-1.  The order within the first k_out-1 entries is ascending page index
+ * per class (above threshold, ties), not score order -- the sparse attention only needs the set and the newest page last. */
+int ob_kv4_page_topk(const void* scores, int32_t* out, int rows, int pitch_sub_chunks, int sub_chunks_per_page,
+                     int total_pages, int k_out, void* stream);
 
 #ifdef __cplusplus
 }

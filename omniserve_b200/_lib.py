@@ -76,6 +76,7 @@ _SIGS = {
     "ob_error_string": ([c_i], C.c_char_p),
     "ob_w4a8_gemm_per_chn": ([c_p] * 7 + [c_i] * 4 + [c_p], c_i),
     "ob_w4a8_gemm_per_group": ([c_p] * 7 + [c_i] * 4 + [c_p], c_i),
+    "ob_w4a8_moe_gemm": ([c_p] * 8 + [c_i] * 5 + [c_p], c_i),
     "ob_w8a8_gemm": ([c_p] * 5 + [c_i] * 4 + [c_p], c_i),
     "ob_w4a8_gemm_ex": ([c_i] + [c_p] * 9 + [c_i] * 7 + [c_p], c_i),
     "ob_w4a8_gemm_add_norm_quant": ([c_i] + [c_p] * 9 + [c_i] * 4 + [c_p] * 6 + [c_f] + [c_p], c_i),
@@ -93,8 +94,10 @@ _SIGS = {
     "ob_add_f16": ([c_p] * 3 + [c_ll] + [c_p], c_i),
     "ob_kv4_single_query_attention": ([C.POINTER(KV4DecodeArgs), c_p], c_i),
     "ob_kv4_apply_rope_update_kv_cache": ([C.POINTER(KV4PrefillArgs), c_p], c_i),
+    "ob_kv4_apply_rope_update_kv_cache_pool": ([C.POINTER(KV4PrefillArgs), c_i, c_p], c_i),
     "ob_compute_padding_offsets": ([c_p] * 2 + [c_i] * 2 + [c_p], c_i),
     "ob_paged_min_max_pool": ([c_p] * 4 + [c_ll] * 2 + [c_i] * 9 + [c_p], c_i),
+    "ob_kv4_page_topk": ([c_p] * 2 + [c_i] * 5 + [c_p], c_i),
     "ob_kv4_page_selector": ([C.POINTER(PageSelectorArgs), c_p], c_i),
 }
 EXPORTS = tuple(_SIGS)

@@ -59,7 +59,10 @@ def single_query(q, k, v, r_tab, s_tab, flags, rank, dyn, lengths, tokens_per_bl
 
 
 def apply_rope_update_kv(qkv, seq_lens, padding_offset, r_tab, s_tab, flags, rank, head_num, kv_head_num, seq_len,
-                         n_r_heads, n_s_heads, sink, local, sink_blk, local_blk, rot_dim, rot_base, rot_scale):
+                         n_r_heads, n_s_heads, sink, local, sink_blk, local_blk, rot_dim, rot_base, rot_scale,
+                         pool_sub_chunk=0):
+    """pool_sub_chunk > 0 (extension): also write the kmax / kmin page statistics of the retrieval heads in the same pass
+    (ob_kv4_apply_rope_update_kv_cache_pool)."""
     L.require_cuda(qkv, seq_lens, padding_offset)
     if not qkv.is_contiguous():
         raise RuntimeError("qkv must be contiguous")
@@ -76,7 +79,11 @@ def apply_rope_update_kv(qkv, seq_lens, padding_offset, r_tab, s_tab, flags, ran
     a.num_retrieval_kv_heads, a.num_streaming_kv_heads = n_r_heads, n_s_heads
     a.sink_token_num, a.local_token_num, a.sink_block_num, a.local_block_num = sink, local, sink_blk, local_blk
     a.rotary_embedding_dim, a.rotary_base, a.rotary_scale = int(rot_dim), float(rot_base), float(rot_scale)
-    L.check(L.lib().ob_kv4_apply_rope_update_kv_cache(C.byref(a), L.stream()), "apply_bias_rope_update_kv_cache")
+    if pool_sub_chunk:
+        L.check(L.lib().ob_kv4_apply_rope_update_kv_cache_pool(C.byref(a), int(pool_sub_chunk), L.stream()),
+                "apply_bias_rope_update_kv_cache + paged_min_max_pool (fused)")
+    else:
+        L.check(L.lib().ob_kv4_apply_rope_update_kv_cache(C.byref(a), L.stream()), "apply_bias_rope_update_kv_cache")
 
 
 def compute_padding_offsets(cu_seqlens, max_seqlen, tot_num_tokens):

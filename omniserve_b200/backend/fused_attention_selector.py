@@ -46,3 +46,18 @@ def single_query_page_selector(q, k, v, retrieval_kv_pointers, streaming_kv_poin
     if padded:
         L.check(L.lib().ob_kv4_page_selector(C.byref(a), L.stream()), "single_query_page_selector")
     return out
+
+
+def page_topk(stats, sub_chunks_per_page, k_out):
+    """Extension: the page choice of decoding_attention.py:132-141 on the device.
+    stats: fp16 [B, Hq, padded_sub_chunks] (output of single_query_page_selector).  Returns int32 [B, Hq, k_out]: the k_out-1
+    best pages among all but the newest (page score = max over its sub-chunks), then the newest page."""
+    import torch
+    L.require_cuda(stats)
+    L.require_contiguous(stats)
+    B, Hq, padded = stats.shape
+    total = padded // sub_chunks_per_page
+    out = torch.empty((B, Hq, k_out), dtype=torch.int32, device=stats.device)
+    L.check(L.lib().ob_kv4_page_topk(L.ptr(stats), L.ptr(out), B * Hq, padded, sub_chunks_per_page, total, k_out, L.stream()),
+            "page_topk")
+    return out

@@ -72,6 +72,14 @@ int ob_w4a8_gemm_per_group(const int8_t* in_feats, const int8_t* kernel, const i
                          ldc, 0, -1, 0, stream);
 }
 
+int ob_w4a8_moe_gemm(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales,
+                     const void* w_szs, const void* a_ssums, void* out_feats, const int* problem_sizes_host, int num_experts,
+                     int T, int N, int K, int ldc, void* stream) {
+  if (!in_feats || !kernel || !wscales || !ascales || !w_szs || !a_ssums || !out_feats || !problem_sizes_host) return OB_ERR_ARG;
+  return w4a8_moe_gemm_run(in_feats, kernel, H(wscales), H(ascales), H(w_szs), H(a_ssums), HM(out_feats), problem_sizes_host,
+                           num_experts, T, N, K, ldc, ST(stream));
+}
+
 int ob_w8a8_gemm(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales, void* out_feats,
                  int M, int N, int K, int ldc, void* stream) {
   if (!in_feats || !kernel || !wscales || !ascales || !out_feats) return OB_ERR_ARG;
@@ -198,6 +206,22 @@ int ob_kv4_apply_rope_update_kv_cache(const ob_kv4_prefill_args* x, void* stream
   return kv4_prefill_write_run(a, ST(stream));
 }
 
+int ob_kv4_apply_rope_update_kv_cache_pool(const ob_kv4_prefill_args* x, int tokens_per_sub_chunk, void* stream) {
+  if (!x || !x->qkv || !x->seq_lens || !x->padding_offset) return OB_ERR_ARG;
+  KV4PrefillArgs a{};
+  a.qkv = HM(x->qkv); a.seq_lens = x->seq_lens; a.padding_offset = x->padding_offset; a.max_seq_len = x->max_seq_len;
+  a.retrieval_kv_pointers = x->retrieval_kv_pointers; a.streaming_kv_pointers = x->streaming_kv_pointers;
+  a.r_max_pages = x->r_max_pages; a.s_max_pages = x->s_max_pages;
+  a.retrieval_head_flags = x->retrieval_head_flags; a.head_rank_table = x->head_rank_table;
+  a.T = x->num_tokens; a.B = x->batch; a.Hq = x->num_heads; a.Hkv = x->num_kv_heads;
+  a.num_retrieval_kv_heads = x->num_retrieval_kv_heads; a.num_streaming_kv_heads = x->num_streaming_kv_heads;
+  a.sink_tokens = x->sink_token_num; a.local_tokens = x->local_token_num;
+  a.sink_blocks = x->sink_block_num; a.local_blocks = x->local_block_num;
+  a.rotary_dim = x->rotary_embedding_dim; a.rotary_base = x->rotary_base;
+  a.rotary_scale = x->rotary_scale != 0.f ? 1.0f / x->rotary_scale : 1.0f;
+  return kv4_prefill_write_pool_run(a, tokens_per_sub_chunk, ST(stream));
+}
+
 int ob_compute_padding_offsets(int32_t* out, const int32_t* cu_seqlens, int batch, int max_seqlen, void* stream) {
   if (!out || !cu_seqlens) return OB_ERR_ARG;
   return padding_offsets_run(out, cu_seqlens, batch, max_seqlen, ST(stream));
@@ -235,6 +259,12 @@ int ob_kv4_page_selector(const ob_page_selector_args* x, void* stream) {
   a.tokens_per_sub_chunk = x->tokens_per_sub_chunk;
   a.hidden_dim_per_retrieval_token = x->hidden_dim_per_retrieval_token;
   return page_selector_run(a, ST(stream));
+}
+
+int ob_kv4_page_topk(const void* scores, int32_t* out, int rows, int pitch_sub_chunks, int sub_chunks_per_page,
+                     int total_pages, int k_out, void* stream) {
+  if (!scores || !out) return OB_ERR_ARG;
+  return page_topk_run(H(scores), out, rows, pitch_sub_chunks, sub_chunks_per_page, total_pages, k_out, ST(stream));
 }
 
 }  // extern "C"

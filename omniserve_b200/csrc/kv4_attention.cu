@@ -788,6 +788,126 @@ __global__ void __launch_bounds__(256) kv4_prefill_write_kernel(const PrefillPar
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused prefill pass: apply_bias_rope_update_kv_cache + paged_min_max_pool in ONE kernel.
+// The reference runs them back to back (omniserve/modeling/layers/ctx_update_kv.py:104-178, llama_w4a8_unpad.py:309-325):
+// the writer rotates q / k in place and writes the KV4 pages, then the pool kernel re-reads the rotated keys of the whole
+// chunk from HBM to build the kmax / kmin page statistics.  Here the work item is one 16-token sub-chunk of one sequence:
+// the CTA rotates and quantises its tokens exactly like kv4_prefill_write_kernel (same arithmetic -> same page bytes), keeps
+// the rotated fp16 keys of the retrieval heads in shared memory and reduces them to the sub-chunk's statistics before moving
+// on -- the keys are read once, and the statistics land in the page the nibbles just went to.
+// ------------------------------------------------------------------------------------------------
+constexpr int FP_SUB = 16;        // tokens per sub-chunk (LServe: 64-token pages, 4 sub-chunks)
+constexpr int FP_MAX_HR = 8;      // retrieval kv heads kept in shared memory
+
+__global__ void __launch_bounds__(256) kv4_prefill_write_pool_kernel(const PrefillParams p, const int B, const long long stats_off_bytes,
+                                                                      const int eles_per_ind) {
+  __shared__ float pw[DH / 2];
+  __shared__ float cs_s[FP_SUB][DH / 2], sn_s[FP_SUB][DH / 2];
+  __shared__ __align__(16) __half kst[FP_SUB][FP_MAX_HR][DH];   // rotated keys of the retrieval heads
+  __shared__ int item_s[4];                                       // b, pos0, n, packed start
+  pdl_trigger();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int heads_total = p.Hq + 2 * p.Hkv;
+  const int row_elems = heads_total * DH;
+  const int half_rot = p.rotary_dim >> 1;
+  if (tid < DH / 2) pw[tid] = powf(p.rope_base, (float)(2 * tid) / (float)p.rotary_dim);
+  pdl_wait();
+  // total number of sub-chunk items
+  int total = 0;
+  for (int b = 0; b < B; ++b) total += (p.seq_lens[b] + FP_SUB - 1) / FP_SUB;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    __syncthreads();
+    if (tid == 0) {
+      int rem = item, start = 0, b = 0;
+      for (; b < B; ++b) {
+        const int L = p.seq_lens[b], c = (L + FP_SUB - 1) / FP_SUB;
+        if (rem < c) break;
+        rem -= c; start += L;
+      }
+      const int L = p.seq_lens[b];
+      item_s[0] = b; item_s[1] = rem * FP_SUB; item_s[2] = min(FP_SUB, L - rem * FP_SUB); item_s[3] = start + rem * FP_SUB;
+    }
+    __syncthreads();
+    const int b = item_s[0], pos0 = item_s[1], n = item_s[2], t0 = item_s[3];
+    const int L = p.seq_lens[b];
+    for (int i = tid; i < n * (DH / 2); i += 256) {
+      const int j = i >> 6, d = i & 63;
+      if (d < half_rot) sincosf(((float)(pos0 + j) * p.rope_scale) / pw[d], &sn_s[j][d], &cs_s[j][d]);
+    }
+    __syncthreads();
+    for (int it = warp; it < n * heads_total; it += 8) {
+      const int j = it / heads_total;
+      const int hh = it - j * heads_total;
+      const int pos = pos0 + j;
+      __half* src = p.qkv + (size_t)(t0 + j) * row_elems + (size_t)hh * DH;
+      const __half2 lo = *reinterpret_cast<const __half2*>(src + 2 * lane);
+      const __half2 hi = *reinterpret_cast<const __half2*>(src + 64 + 2 * lane);
+      float x[4] = {__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi)};
+      const bool is_v = hh >= p.Hq + p.Hkv;
+      if (!is_v) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int d = 2 * lane + e;
+          if (d < half_rot) {
+            const float sn = sn_s[j][d], cs = cs_s[j][d];
+            const float a = x[e], bb = x[2 + e];
+            x[e] = __half2float(__float2half_rn(cs * a - sn * bb));
+            x[2 + e] = __half2float(__float2half_rn(cs * bb + sn * a));
+          }
+        }
+        *reinterpret_cast<__half2*>(src + 2 * lane) = __floats2half2_rn(x[0], x[1]);
+        *reinterpret_cast<__half2*>(src + 64 + 2 * lane) = __floats2half2_rn(x[2], x[3]);
+      }
+      if (hh < p.Hq) continue;
+      const int hkv = is_v ? hh - p.Hq - p.Hkv : hh - p.Hq;
+      const bool retr = p.retrieval_flags ? p.retrieval_flags[hkv] != 0 : true;
+      const int rank = p.head_rank ? p.head_rank[hkv] : hkv;
+      if (!is_v && retr) {
+        *reinterpret_cast<__half2*>(&kst[j][rank][2 * lane]) = __floats2half2_rn(x[0], x[1]);
+        *reinterpret_cast<__half2*>(&kst[j][rank][64 + 2 * lane]) = __floats2half2_rn(x[2], x[3]);
+      }
+      int tabidx = pos >> 6;
+      const int64_t* tab;
+      int hpool;
+      if (retr) {
+        tab = p.r_tab + (size_t)b * 2 * p.r_max_pages + (is_v ? p.r_max_pages : 0);
+        hpool = p.r_hpool;
+      } else {
+        if (!(pos < p.sink_tok || pos >= L - p.local_tok)) continue;  // applyBiasRopeUpdateKVCache.h:303-311
+        tab = p.s_tab + (size_t)b * 2 * p.s_max_pages + (is_v ? p.s_max_pages : 0);
+        hpool = p.s_hpool;
+        tabidx = tabidx < p.sink_blk ? tabidx : p.sink_blk + (tabidx - p.sink_blk) % p.local_blk;
+      }
+      uint8_t* page = reinterpret_cast<uint8_t*>(tab[tabidx]);
+      const int slot = pos & 63;
+      const int data_bytes = hpool * TPB * (DH / 2);
+      __half* sc = reinterpret_cast<__half*>(page + data_bytes) + rank * TPB + slot;
+      quant_store_pairs(x, page + (size_t)rank * TPB * (DH / 2) + slot * (DH / 2), sc, sc + hpool * TPB, lane);
+    }
+    __syncthreads();
+    // statistics of this sub-chunk: channel-wise max / min over its valid tokens (context_pool_kernel.cu:16-69)
+    if (p.r_hpool > 0 && p.r_tab) {
+      uint8_t* kpage = reinterpret_cast<uint8_t*>(p.r_tab[(size_t)b * 2 * p.r_max_pages + (pos0 >> 6)]);
+      const int sub_idx = (pos0 & 63) / FP_SUB;
+      __half* kmax = reinterpret_cast<__half*>(kpage + stats_off_bytes) + (size_t)sub_idx * eles_per_ind;
+      __half* kmin = kmax + (size_t)(TPB / FP_SUB) * eles_per_ind;
+      for (int col = tid; col < p.r_hpool * (DH / 2); col += 256) {
+        const int r = col / (DH / 2), d2 = col - r * (DH / 2);
+        __half2 mx = *reinterpret_cast<const __half2*>(&kst[0][r][2 * d2]);
+        __half2 mn = mx;
+        for (int j = 1; j < n; ++j) {
+          const __half2 v = *reinterpret_cast<const __half2*>(&kst[j][r][2 * d2]);
+          mx = __hmax2(mx, v);
+          mn = __hmin2(mn, v);
+        }
+        *reinterpret_cast<__half2*>(kmax + r * DH + 2 * d2) = mx;
+        *reinterpret_cast<__half2*>(kmin + r * DH + 2 * d2) = mn;
+      }
+    }
+  }
+}
+
 __global__ void padding_offsets_kernel(int* out, const int* cu, int max_seq_len) {
   const int b = blockIdx.x;
   const int beg = cu[b], end = cu[b + 1];
@@ -923,6 +1043,27 @@ int padding_offsets_run(int* out, const int* cu_seqlens, int B, int max_seq_len,
   if (B <= 0) return 0;
   padding_offsets_kernel<<<B, 256, 0, st>>>(out, cu_seqlens, max_seq_len);
   return cudaGetLastError() == cudaSuccess ? 0 : OB_ERR_CUDA;
+}
+
+int kv4_prefill_write_pool_run(const KV4PrefillArgs& a, int tokens_per_sub_chunk, cudaStream_t st) {
+  if (a.T <= 0) return 0;
+  if (a.rotary_dim != DH || tokens_per_sub_chunk != FP_SUB || a.num_retrieval_kv_heads > FP_MAX_HR || a.B <= 0) return OB_ERR_SHAPE;
+  PrefillParams p{};
+  p.qkv = a.qkv; p.seq_lens = a.seq_lens; p.padding_offset = a.padding_offset; p.max_seq_len = a.max_seq_len;
+  p.r_tab = a.retrieval_kv_pointers; p.s_tab = a.streaming_kv_pointers;
+  p.r_max_pages = a.r_max_pages; p.s_max_pages = a.s_max_pages;
+  p.retrieval_flags = a.retrieval_head_flags; p.head_rank = a.head_rank_table;
+  p.T = a.T; p.Hq = a.Hq; p.Hkv = a.Hkv; p.r_hpool = a.num_retrieval_kv_heads; p.s_hpool = a.num_streaming_kv_heads;
+  p.sink_tok = a.sink_tokens; p.local_tok = a.local_tokens; p.sink_blk = a.sink_blocks;
+  p.local_blk = a.local_blocks > 0 ? a.local_blocks : 1;
+  p.rotary_dim = a.rotary_dim; p.rope_base = a.rotary_base; p.rope_scale = a.rotary_scale;
+  // K page: [H][64][64] nibbles | scales f16 [H][64] | zeros f16 [H][64] | kmax f16 [4][H*128] | kmin
+  const long long stats_off = (long long)a.num_retrieval_kv_heads * TPB * (DH / 2) + (long long)a.num_retrieval_kv_heads * TPB * 4;
+  const int eles = a.num_retrieval_kv_heads * DH;
+  const int items = (a.T + FP_SUB - 1) / FP_SUB + a.B;
+  const int blocks = std::min(items, 148 * 4);
+  return launch_pdl(kv4_prefill_write_pool_kernel, dim3(blocks), dim3(256), 0, st, p, a.B, stats_off, eles) == cudaSuccess
+             ? 0 : OB_ERR_CUDA;
 }
 
 }  // namespace ob

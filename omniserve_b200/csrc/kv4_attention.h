@@ -46,6 +46,8 @@ struct KV4PrefillArgs {
   int rotary_dim; float rotary_base; float rotary_scale;
 };
 int kv4_prefill_write_run(const KV4PrefillArgs& a, cudaStream_t st);
+// fused: the same page writes + the kmax / kmin statistics of every 16-token sub-chunk of the retrieval heads
+int kv4_prefill_write_pool_run(const KV4PrefillArgs& a, int tokens_per_sub_chunk, cudaStream_t st);
 int padding_offsets_run(int* out, const int* cu_seqlens, int B, int max_seq_len, cudaStream_t st);
 
 }  // namespace ob

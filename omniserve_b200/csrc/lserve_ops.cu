@@ -257,4 +257,110 @@ int page_selector_run(const SelectorArgs& a, cudaStream_t st) {
 #undef OB_SEL
 }
 
+// ------------------------------------------------------------------------------------------------ page top-k
+// The page choice the reference makes in PyTorch after the selector (decoding_attention.py:132-141):
+//   page score = max over the page's 4 sub-chunk scores; keep the k-1 best pages among all but the newest; append the
+//   newest page; int32.  One CTA per (sequence, q-head): fp16 scores are mapped to order-preserving 16-bit keys and the
+//   (k-1)-th largest is found with two 256-bin radix passes over shared memory; pages strictly above the threshold are
+//   emitted first, ties at the threshold in page order (torch.topk's tie order is unspecified; the attention only needs the
+//   SET and the newest page last).  Output order: ascending page index within each class -- deterministic.
+constexpr int TOPK_THREADS = 256;
+
+OB_DEVICE uint32_t f16_key(__half h) {   // order-preserving map fp16 -> [0, 65535]; -0 < +0, NaNs sort to the ends
+  const uint32_t u = __half_as_ushort(h);
+  return (u & 0x8000u) ? (0xFFFFu - u) : (u | 0x8000u);
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS) page_topk_kernel(const __half* __restrict__ scores, int* __restrict__ out,
+                                                                   const int pitch /*sub-chunks per row*/, const int group /*per page*/,
+                                                                   const int total_pages, const int k_out) {
+  extern __shared__ uint16_t keys[];          // [total_pages - 1]
+  __shared__ int hist[256];
+  __shared__ int sel[4];                      // threshold bin bookkeeping
+  __shared__ int warp_cnt[2][TOPK_THREADS / 32];
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __half* src = scores + (size_t)row * pitch;
+  int* dst = out + (size_t)row * k_out;
+  const int n = total_pages - 1;              // candidates: every page but the newest
+  const int k = k_out - 1;                    // how many of them to keep
+  if (tid == 0) dst[k_out - 1] = total_pages - 1;
+  if (k <= 0) return;
+  for (int pg = tid; pg < n; pg += TOPK_THREADS) {
+    __half m = src[pg * group];
+    for (int j = 1; j < group; ++j) m = __hmax(m, src[pg * group + j]);
+    keys[pg] = (uint16_t)f16_key(m);
+  }
+  // pass 1: high byte
+  for (int i = tid; i < 256; i += TOPK_THREADS) hist[i] = 0;
+  __syncthreads();
+  for (int pg = tid; pg < n; pg += TOPK_THREADS) atomicAdd(&hist[keys[pg] >> 8], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0, b = 255;
+    for (; b >= 0; --b) { if (acc + hist[b] >= k) break; acc += hist[b]; }
+    sel[0] = b; sel[1] = acc;                 // `acc` keys lie in bins above b
+  }
+  __syncthreads();
+  const int hb = sel[0], above_hi = sel[1];
+  __syncthreads();
+  // pass 2: low byte inside the threshold bin
+  for (int i = tid; i < 256; i += TOPK_THREADS) hist[i] = 0;
+  __syncthreads();
+  for (int pg = tid; pg < n; pg += TOPK_THREADS)
+    if ((keys[pg] >> 8) == hb) atomicAdd(&hist[keys[pg] & 0xFF], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int acc = above_hi, b = 255;
+    for (; b >= 0; --b) { if (acc + hist[b] >= k) break; acc += hist[b]; }
+    sel[2] = (hb << 8) | b;                   // threshold key
+    sel[3] = acc;                             // keys strictly above the threshold
+  }
+  __syncthreads();
+  const int thr = sel[2], n_above = sel[3];
+  // emit: pages above the threshold first, then ties in page order; slots from a block-wide exclusive scan
+  int base_a = 0, base_t = 0;
+  for (int p0 = 0; p0 < n; p0 += TOPK_THREADS) {
+    const int pg = p0 + tid;
+    const int key = pg < n ? keys[pg] : -1;
+    const bool is_a = key > thr, is_t = key == thr;
+    const unsigned ma = __ballot_sync(0xffffffffu, is_a), mt = __ballot_sync(0xffffffffu, is_t);
+    if (lane == 0) { warp_cnt[0][warp] = __popc(ma); warp_cnt[1][warp] = __popc(mt); }
+    __syncthreads();
+    int off_a = base_a, off_t = base_t, tot_a = 0, tot_t = 0;
+    for (int w = 0; w < TOPK_THREADS / 32; ++w) {
+      if (w < warp) { off_a += warp_cnt[0][w]; off_t += warp_cnt[1][w]; }
+      tot_a += warp_cnt[0][w]; tot_t += warp_cnt[1][w];
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    if (is_a) dst[off_a + __popc(ma & lt)] = pg;
+    if (is_t) {
+      const int slot = n_above + off_t + __popc(mt & lt);
+      if (slot < k) dst[slot] = pg;
+    }
+    base_a += tot_a; base_t += tot_t;
+    __syncthreads();
+  }
+}
+
+int page_topk_run(const __half* scores, int* out, int rows, int pitch_sub_chunks, int sub_chunks_per_page, int total_pages,
+                  int k_out, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (total_pages <= 0 || k_out <= 0 || k_out > total_pages || sub_chunks_per_page <= 0 ||
+      pitch_sub_chunks < total_pages * sub_chunks_per_page)
+    return OB_ERR_SHAPE;
+  const size_t smem = (size_t)std::max(1, total_pages - 1) * 2;
+  if (smem > 200 * 1024) return OB_ERR_SHAPE;   // > 100K pages (6.5M tokens)
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 16 && !attr_done[dev] && smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(page_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return OB_ERR_CUDA;
+    attr_done[dev] = true;
+  }
+  return launch_pdl(page_topk_kernel, dim3(rows), dim3(TOPK_THREADS), smem, st, scores, out, pitch_sub_chunks, sub_chunks_per_page,
+                    total_pages, k_out) == cudaSuccess ? 0 : OB_ERR_CUDA;
+}
+
 }  // namespace ob

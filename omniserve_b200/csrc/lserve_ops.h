@@ -34,4 +34,10 @@ struct SelectorArgs {
 };
 int page_selector_run(const SelectorArgs& a, cudaStream_t st);
 
+// Device-side page choice after the selector (decoding_attention.py:132-141): scores fp16 [rows, pitch] sub-chunk scores,
+// out int32 [rows, k_out] = the k_out-1 best pages among pages 0..total_pages-2 (page score = max of its sub-chunks) followed
+// by the newest page total_pages-1.
+int page_topk_run(const __half* scores, int* out, int rows, int pitch_sub_chunks, int sub_chunks_per_page, int total_pages,
+                  int k_out, cudaStream_t st);
+
 }  // namespace ob

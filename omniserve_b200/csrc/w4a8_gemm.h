@@ -39,6 +39,11 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st);
 // force_ctas = grid override (0 = auto).  Returns OB_ERR_SHAPE for shapes it does not take (caller falls back).
 int w4a8_gemm_decode_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st);
 
+// Grouped (mixture-of-experts) W4A8 per-channel GEMM (w4a8_gemm_decode.cu), see include/omniserve_b200.h.
+int w4a8_moe_gemm_run(const int8_t* x, const int8_t* qweight, const __half* wscales, const __half* ascales, const __half* w_szs,
+                      const __half* a_ssums, __half* out, const int* problem_sizes_host, int num_experts, int T, int N, int K,
+                      int ldc, cudaStream_t st);
+
 // W8A8 GEMM (w8a8_gemm.cu): out = (in . W^T) * wscales[n] * ascales[m], W plain row-major [N, K] int8.
 int w8a8_gemm_run(const int8_t* in_feats, const int8_t* weight, const __half* wscales, const __half* ascales, __half* out,
                   int M, int N, int K, int ldc, cudaStream_t st);

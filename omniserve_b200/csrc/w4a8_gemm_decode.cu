@@ -66,8 +66,17 @@ struct Params {
   int32_t* counters;  // [grid]
   int M, N, K, ldc;
   int n_tiles, kb_per_tile, units_per_cta;
+  int n_tiles_e;      // grouped mode: n-tiles per expert (n_tiles = groups * n_tiles_e)
   long long* dbg_t;   // -DOB_DEC_TIMING builds only (tools/dec_waits.py): [grid][32] globaltimer stamps
 };
+
+// Grouped (mixture-of-experts) mode: the virtual tile index runs over (group, n-tile); a group is up to BN consecutive
+// token rows routed to one expert (w4a8_moe_linear.py:83-94: x sorted by expert, `problem_sizes` rows per expert).
+constexpr int MOE_MAX_GROUPS = 64;
+struct MoeTab { int expert[MOE_MAX_GROUPS]; int row0[MOE_MAX_GROUPS]; int rows[MOE_MAX_GROUPS]; };
+struct NoMoe {};
+template <bool MOE> struct MoeSel { using type = NoMoe; };
+template <> struct MoeSel<true> { using type = MoeTab; };
 
 struct Seg { int tile, kb0, kb1; };
 
@@ -109,9 +118,10 @@ OB_DEVICE void red_add_s32(int32_t* addr, int32_t v) {
 }
 OB_DEVICE void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the eight unpack / epilogue warps
 
-template <int BN, bool PER_GROUP>
+template <int BN, bool PER_GROUP, bool MOE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
-w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_constant__ CUtensorMap w_map, const Params p) {
+w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_constant__ CUtensorMap w_map, const Params p,
+                        const __grid_constant__ typename MoeSel<MOE>::type moe) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -162,12 +172,17 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       int stage = 0, phase = 0;
       while (it.next(sg)) {
         const int n_cnt = min(BM, p.N - sg.tile * BM);
+        int w_tile = sg.tile;     // row-of-tiles coordinate in the packed weight tensor
+        if constexpr (MOE) {
+          const int g = sg.tile / p.n_tiles_e;
+          w_tile = moe.expert[g] * p.n_tiles_e + (sg.tile - g * p.n_tiles_e);   // experts are stacked along N
+        }
         for (int kb = sg.kb0; kb < sg.kb1; kb += KPS) {
           const int cnt = min(KPS, sg.kb1 - kb);
           mbar_wait(&w_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&w_full[stage], cnt * (W_KB + (PER_GROUP ? 2 * n_cnt : 0)));
           for (int j = 0; j < cnt; ++j) {
-            tma_load_3d(sW + stage * C::W_STAGE + j * W_KB, &w_map, 0, (kb + j) * 4, sg.tile * 4, &w_full[stage]);
+            tma_load_3d(sW + stage * C::W_STAGE + j * W_KB, &w_map, 0, (kb + j) * 4, w_tile * 4, &w_full[stage]);
             if (PER_GROUP) {
               uint8_t* d = sS2 + stage * C::S2_STAGE + j * S2_KB;
               bulk_g2s(d, p.s2_scales + (size_t)(kb + j) * p.N + sg.tile * BM, n_cnt, &w_full[stage]);
@@ -186,12 +201,14 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       Seg sg;
       int stage = 0, phase = 0;
       while (it.next(sg)) {
+        int row0 = 0;
+        if constexpr (MOE) row0 = moe.row0[sg.tile / p.n_tiles_e];
         for (int kb = sg.kb0; kb < sg.kb1; kb += KPS) {
           const int cnt = min(KPS, sg.kb1 - kb);
           mbar_wait(&ba_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&b_full[stage], cnt * BN * BK);
           for (int j = 0; j < cnt; ++j)
-            tma_load_2d(sB + stage * C::B_STAGE + j * BN * BK, &act_map, (kb + j) * BK, 0, &b_full[stage]);
+            tma_load_2d(sB + stage * C::B_STAGE + j * BN * BK, &act_map, (kb + j) * BK, row0, &b_full[stage]);
           if (++stage == AB_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -314,18 +331,25 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
         waited = true;
         if (warp == 4) OB_GT(27);   // grid dependency resolved
       }
-      const int nt = sg.tile;
+      int nt = sg.tile, m_rows = p.M, row0 = 0, s_off = 0;   // grouped mode: this tile's token rows and expert
+      if constexpr (MOE) {
+        const int g = sg.tile / p.n_tiles_e;
+        nt = sg.tile - g * p.n_tiles_e;
+        m_rows = moe.rows[g];
+        row0 = moe.row0[g];
+        s_off = moe.expert[g] * p.N;
+      }
       const int n_row = nt * BM + q * 32 + lane;
       const bool n_ok = n_row < p.N;
       const bool full_tile = (sg.kb0 == 0 && sg.kb1 == p.kb_per_tile);
       float wsc = 0.f, wsz = 0.f;
       if (n_ok) {
-        wsc = __half2float(p.wscales[n_row]);
-        if (!PER_GROUP) wsz = __half2float(p.w_szs[n_row]);
+        wsc = __half2float(p.wscales[s_off + n_row]);
+        if (!PER_GROUP) wsz = __half2float(p.w_szs[s_off + n_row]);
       }
       if (et < BN) {
-        sTok[et] = (et < p.M) ? __half2float(p.ascales[et]) : 0.f;
-        sTok[BN + et] = (!PER_GROUP && et < p.M) ? __half2float(p.a_ssums[et]) : 0.f;
+        sTok[et] = (et < m_rows) ? __half2float(p.ascales[row0 + et]) : 0.f;
+        sTok[BN + et] = (!PER_GROUP && et < m_rows) ? __half2float(p.a_ssums[row0 + et]) : 0.f;
       }
       mbar_wait(acc_full, acc_phase);
       if (warp == 4) OB_GT(28);     // accumulator of the (last) segment complete
@@ -335,7 +359,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       constexpr int HALF = BN / 2;                       // tokens per set
       constexpr int CH = HALF >= 16 ? 16 : 8;            // columns per tcgen05.ld
       const int c_base = set * HALF;
-      const int first_cta = (int)(((long long)nt * p.kb_per_tile) / p.units_per_cta);
+      const int first_cta = (int)(((long long)sg.tile * p.kb_per_tile) / p.units_per_cta);
       int32_t* slot = p.ws + (size_t)first_cta * (BN * BM);
 #pragma unroll 1
       for (int c0 = c_base; c0 < c_base + HALF; c0 += CH) {
@@ -357,7 +381,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
             float o;
             if (PER_GROUP) o = ps * (wsc * sTok[m]);
             else o = __fmaf_rn(-wsz, sTok[BN + m], (ps * wsc) * sTok[m]);
-            if (n_ok && m < p.M) p.out[(size_t)m * p.ldc + n_row] = __float2half_rn(o);
+            if (n_ok && m < m_rows) p.out[(size_t)(row0 + m) * p.ldc + n_row] = __float2half_rn(o);
           }
         } else {
 #pragma unroll
@@ -369,7 +393,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       if (lane == 0) mbar_arrive(acc_empty);    // MMAs of the next segment may overwrite the accumulator
       if (!full_tile) {
         // exact INT32 split-K: every contributor's reds must be performed before its arrival is counted
-        const int last_cta = (int)(((long long)(nt + 1) * p.kb_per_tile - 1) / p.units_per_cta);
+        const int last_cta = (int)(((long long)(sg.tile + 1) * p.kb_per_tile - 1) / p.units_per_cta);
         const int contributors = last_cta - first_cta + 1;
         __threadfence();
         bar_epi();
@@ -395,7 +419,7 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
               float o;
               if (PER_GROUP) o = ps * (wsc * sTok[m]);
               else o = __fmaf_rn(-wsz, sTok[BN + m], (ps * wsc) * sTok[m]);
-              if (n_ok && m < p.M) p.out[(size_t)m * p.ldc + n_row] = __float2half_rn(o);
+              if (n_ok && m < m_rows) p.out[(size_t)(row0 + m) * p.ldc + n_row] = __float2half_rn(o);
             }
           }
           if (et == 0) p.counters[first_cta] = 0;
@@ -412,10 +436,10 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
   if (warp == 3) OB_GT(30);   // exit
 }
 
-template <int BN, bool PG>
-static int launch(const CUtensorMap& amap, const CUtensorMap& wmap, const Params& p, int grid, cudaStream_t st) {
+template <int BN>
+static int launch_moe(const CUtensorMap& amap, const CUtensorMap& wmap, const Params& p, const MoeTab& tab, int grid, cudaStream_t st) {
   using C = Cfg<BN>;
-  auto kern = w4a8_gemm_decode_kernel<BN, PG>;
+  auto kern = w4a8_gemm_decode_kernel<BN, false, true>;
   static bool attr_done[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -423,7 +447,21 @@ static int launch(const CUtensorMap& amap, const CUtensorMap& wmap, const Params
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL) != cudaSuccess) return OB_ERR_CUDA;
     attr_done[dev] = true;
   }
-  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, amap, wmap, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
+  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, amap, wmap, p, tab) == cudaSuccess ? 0 : OB_ERR_CUDA;
+}
+
+template <int BN, bool PG>
+static int launch(const CUtensorMap& amap, const CUtensorMap& wmap, const Params& p, int grid, cudaStream_t st) {
+  using C = Cfg<BN>;
+  auto kern = w4a8_gemm_decode_kernel<BN, PG, false>;
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL) != cudaSuccess) return OB_ERR_CUDA;
+    attr_done[dev] = true;
+  }
+  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, amap, wmap, p, NoMoe{}) == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
 
 }  // namespace dec
@@ -498,6 +536,62 @@ int w4a8_gemm_decode_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st)
     case 32: return per_group ? launch<32, true>(amap, wmap, p, grid, st) : launch<32, false>(amap, wmap, p, grid, st);
     default: return per_group ? launch<64, true>(amap, wmap, p, grid, st) : launch<64, false>(amap, wmap, p, grid, st);
   }
+}
+
+// Grouped W4A8 per-channel GEMM for mixture-of-experts layers (interface of the reference's
+// unreleased op, w4a8_moe_linear.py:83-94: x [T, K] int8 with the token rows sorted by expert, qweight [E, N, K/2] in the
+// reference tile layout per expert, s1_scales / s1_szeros [E, N], per-token input_scales / input_sum [T], problem_sizes[e] =
+// rows routed to expert e; out [T, N] fp16).  One launch: every (expert chunk of <= 64 rows, 128-row weight tile) is a
+// whole-K tile of the decode kernel -- no split, weights streamed once per chunk.
+int w4a8_moe_gemm_run(const int8_t* x, const int8_t* qweight, const __half* wscales, const __half* ascales, const __half* w_szs,
+                      const __half* a_ssums, __half* out, const int* problem_sizes_host, int num_experts, int T, int N, int K,
+                      int ldc, cudaStream_t st) {
+  using namespace dec;
+  if (T <= 0 || num_experts <= 0) return 0;
+  if (N % BM != 0 || K % BK != 0 || ldc < N) return OB_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(qweight) & 15)) return OB_ERR_ALIGN;
+  long long tot = 0;
+  for (int e = 0; e < num_experts; ++e) {
+    if (problem_sizes_host[e] < 0) return OB_ERR_ARG;
+    tot += problem_sizes_host[e];
+  }
+  if (tot != T) return OB_ERR_ARG;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return OB_ERR_ARG;
+  const int sms = dev_sms(dev);
+  int32_t* ws = nullptr;
+  int32_t* cnt = nullptr;
+  if (int e = get_workspace(dev, st, &ws, &cnt)) return e;
+  CUtensorMap amap, wmap;
+  if (int e = make_act_map(&amap, x, T, K, 64)) return e;
+  if (int e = make_w_map(&wmap, qweight, num_experts * N, K, false)) return e;   // experts stacked along N
+  Params p{};
+  p.wscales = wscales; p.ascales = ascales; p.w_szs = w_szs; p.a_ssums = a_ssums; p.out = out; p.ws = ws; p.counters = cnt;
+  p.M = 64; p.N = N; p.K = K; p.ldc = ldc;
+  p.n_tiles_e = N / BM;
+  p.kb_per_tile = K / BK;
+  // chunks of <= 64 rows per expert, launched MOE_MAX_GROUPS at a time
+  MoeTab tab{};
+  int g = 0, row = 0;
+  auto flush = [&]() -> int {
+    if (g == 0) return 0;
+    p.n_tiles = g * p.n_tiles_e;
+    const int tiles_per_cta = (p.n_tiles + 2 * sms - 1) / (2 * sms);
+    p.units_per_cta = tiles_per_cta * p.kb_per_tile;     // whole tiles per CTA: no split-K
+    const int grid = (p.n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    const int e = launch_moe<64>(amap, wmap, p, tab, grid, st);
+    g = 0;
+    return e;
+  };
+  for (int e = 0; e < num_experts; ++e) {
+    for (int done = 0; done < problem_sizes_host[e]; done += 64) {
+      tab.expert[g] = e; tab.row0[g] = row + done; tab.rows[g] = std::min(64, problem_sizes_host[e] - done);
+      if (++g == MOE_MAX_GROUPS) { if (int err = flush()) return err; }
+    }
+    row += problem_sizes_host[e];
+  }
+  return flush();
 }
 
 }  // namespace ob

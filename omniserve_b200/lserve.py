@@ -29,6 +29,7 @@ class SparseDecodeConfig:
     rotary_base: float = 500000.0
     rope_scaling_factor: float = 1.0
     multiblock_switch: int = 2048
+    device_topk: bool = True              # page choice on the device (csrc/lserve_ops.cu: page_topk_kernel) instead of torch ops
 
 
 def paged_min_max_pool(keys, retrieval_block_table, cu_seqlens, max_seq_len, pooling_heads_idx, num_retrieval_kv_heads,
@@ -55,10 +56,15 @@ def dynamic_select_topk_pages(q, k, v, retrieval_block_table, streaming_block_ta
         lengths_per_sample, None, cfg.memory_max_len, tpb, size_r, size_s, sink_size, local_size, sink_blocks,
         local_blocks, num_retrieval_kv_heads, num_streaming_kv_heads, timestep, cfg.head_dim, cfg.rotary_base,
         cfg.rope_scaling_factor, True, True, True, cfg.sub_chunk_size, num_retrieval_kv_heads * cfg.head_dim, 1000000)
-    stats = stats.view(q.shape[0], q.shape[1], -1, tpb // cfg.sub_chunk_size)
+    group = tpb // cfg.sub_chunk_size
+    total = stats.shape[-1] // group
+    k_out = min(max(3, budget // tpb), total)
+    if cfg.device_topk:
+        # one kernel instead of the reference's view / max / topk / cat / to(int32) chain (decoding_attention.py:132-141)
+        return fused_attention_selector.page_topk(stats, group, k_out)
+    stats = stats.view(q.shape[0], q.shape[1], -1, group)
     stats = torch.max(stats, dim=-1).values
-    total = stats.size(-1)
-    _, idx = stats[:, :, :-1].topk(k=(min(max(3, budget // tpb), total) - 1), dim=-1)
+    _, idx = stats[:, :, :-1].topk(k=k_out - 1, dim=-1)
     idx = torch.cat([idx, torch.ones_like(idx[..., :1]) * (total - 1)], dim=-1).contiguous()
     return idx.to(torch.int32)
 

@@ -208,6 +208,25 @@ def gemm_w8a8(in_feats, weight, wscales, ascales):
     return acc, out.astype(np.float16)
 
 
+def moe_gemm_per_chn(x, qweights, wscales, ascales, w_szs, a_ssums, problem_sizes):
+    """Grouped per-channel GEMM of a mixture-of-experts layer (interface of w4a8_moe_linear.py:83-94; the reference never
+    released the kernel, so this restates the only possible semantics: rows of ``x`` are sorted by expert, expert ``e`` owns
+    ``problem_sizes[e]`` consecutive rows and applies :func:`gemm_per_chn` with its own packed weight / scales).
+    x int8 [T,K]; qweights int8 [E,N,K/2]; wscales, w_szs f16 [E,N]; ascales, a_ssums f16 [T].  Returns f16 [T,N]."""
+    x = np.asarray(x, np.int8)
+    E, N = np.asarray(wscales).shape
+    out = np.zeros((x.shape[0], N), np.float16)
+    r = 0
+    for e in range(E):
+        m = int(problem_sizes[e])
+        if m:
+            _, o = gemm_per_chn(x[r:r + m], qweights[e], wscales[e], ascales[r:r + m], w_szs[e], a_ssums[r:r + m])
+            out[r:r + m] = o
+        r += m
+    assert r == x.shape[0]
+    return out
+
+
 def roundtrip_per_channel(w: np.ndarray):
     """Returns (w_fake, w_roundtrip, packed).  ``w_roundtrip`` must equal ``w_fake`` exactly."""
     w_fake, scales, zeros = pseudo_quantize_tensor(w, n_bit=4, q_group_size=-1)

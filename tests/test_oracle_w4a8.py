@@ -117,3 +117,21 @@ def test_w8a8_oracle_matches_plain_definition():
     np.testing.assert_array_equal(acc, a.astype(np.int64) @ w.astype(np.int64).T)
     want = (acc.astype(np.float32) * (ws.astype(np.float32)[None, :] * sa.astype(np.float32)[:, None])).astype(np.float16)
     np.testing.assert_array_equal(out, want)
+
+
+def test_moe_oracle_applies_each_experts_gemm_to_its_rows():
+    from oracle import w4a8 as ow
+    rng = np.random.default_rng(4)
+    E, N, K, sizes = 3, 64, 256, [2, 0, 5]
+    q = rng.integers(0, 16, (E, N, K), dtype=np.uint8)
+    qw = np.stack([ow.pack_w4(q[e]) for e in range(E)])
+    x = rng.integers(-127, 128, (7, K), dtype=np.int8)
+    s1 = rng.uniform(0.005, 0.02, (E, N)).astype(np.float16)
+    szs = (8 * s1.astype(np.float32)).astype(np.float16)
+    sa = rng.uniform(0.01, 0.05, 7).astype(np.float16)
+    ss = rng.standard_normal(7).astype(np.float16)
+    out = ow.moe_gemm_per_chn(x, qw, s1, sa, szs, ss, sizes)
+    _, o0 = ow.gemm_per_chn(x[:2], qw[0], s1[0], sa[:2], szs[0], ss[:2])
+    _, o2 = ow.gemm_per_chn(x[2:], qw[2], s1[2], sa[2:], szs[2], ss[2:])
+    np.testing.assert_array_equal(out[:2], o0)
+    np.testing.assert_array_equal(out[2:], o2)
