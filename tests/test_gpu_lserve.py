@@ -332,3 +332,38 @@ def test_c3_shape_256k_context_head_split_from_fixture():
               f"|ref-exact|={e_ref:.3e} |ours-ref|={np.abs(got - ref_out).max() / sc_:.3e}")
         assert np.abs(got - exact).max() / sc_ <= max(e_ref, 5e-3)
         assert np.abs(got - ref_out).max() / sc_ <= 5e-2
+
+
+def test_lserve_decoder_graph_replay_equals_eager_small():
+    """omniserve_b200/lserve_model.py (the C3 bench's model): graph-replayed sparse decode step == eager step, selector and
+    reuse variants, on a small stack with a mixed retrieval / streaming head split."""
+    from omniserve_b200.lserve_model import LServeDecodeGraphs, LServeDecoder
+    from omniserve_b200.model import LlamaConfig
+    cfg = LlamaConfig(hidden_size=1024, intermediate_size=2048, num_hidden_layers=2, num_attention_heads=8, num_key_value_heads=4,
+                      vocab_size=2048)
+    flags = [[1, 0, 1, 1], [0, 1, 1, 0]]
+    ctx = 6000                                  # > the 4096-token budget: the selector path is taken
+    outs = []
+    for use_graph in (False, True):
+        dec = LServeDecoder(cfg, flags, "cuda", token_budget=1024)
+        dec.alloc(ctx + 64)
+        torch.manual_seed(0)
+        dec.fill_random(ctx)
+        tok = torch.tensor([5], device="cuda")
+        if use_graph:
+            gr = LServeDecodeGraphs(dec, ctx)
+            gr.tokens.copy_(tok)
+            a = gr.step(True).clone()
+            gr.tokens.copy_(tok)
+            b = gr.step(False).clone()
+        else:
+            saved = dec.context_lens.clone()
+            a = dec.decode_step(tok, ctx, True).clone()
+            dec.context_lens.copy_(saved)
+            b = dec.decode_step(tok, ctx, False).clone()
+        torch.cuda.synchronize()
+        outs.append((a, b, [d.clone() for d in dec.dyn]))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for x, y in zip(outs[0][2], outs[1][2]):
+        assert torch.equal(x, y)
+        assert int(x[..., -1].min()) == (ctx - 1) // 64 == int(x[..., -1].max())
