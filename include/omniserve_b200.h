@@ -161,6 +161,10 @@ typedef struct ob_kv4_decode_args {
    * a decode loop); the kernel then streams those pages while its predecessor is still draining (programmatic dependent
    * launch).  0 = read nothing before the stream dependency has resolved (safe right after a prefill write). */
   int history_is_stable;
+  /* Per-tensor KV8 mode (fused_attention_per_tensor/{dense,sparse}_attention/fused_attention.cpp: single_query_attention
+   * takes kv_scale_quant_orig / kv_scale_orig_quant, float[2] = K, V): both non-NULL = the pages hold INT8 codes
+   * [H_pool][64][128] (size_per_token = H_pool * 128) with static per-tensor scales; NULL = the KV4 pages above. */
+  const float* kv_scale_quant_orig; const float* kv_scale_orig_quant;
 } ob_kv4_decode_args;
 int ob_kv4_single_query_attention(const ob_kv4_decode_args* args, void* stream);
 
@@ -177,6 +181,9 @@ typedef struct ob_kv4_prefill_args {
   int num_retrieval_kv_heads, num_streaming_kv_heads;
   int sink_token_num, local_token_num, sink_block_num, local_block_num;
   int rotary_embedding_dim; float rotary_base; float rotary_scale;
+  /* Per-tensor KV8 mode (per_tensor_common/update_kv_cache.cu:27-): non-NULL float[2] (K, V) = write INT8 pages
+   * cvt.rni.sat(x * scale) instead of KV4; NULL = KV4.  Not supported by the _pool variant (OB_ERR_ARG). */
+  const float* kv_scale_orig_quant;
 } ob_kv4_prefill_args;
 int ob_kv4_apply_rope_update_kv_cache(const ob_kv4_prefill_args* args, void* stream);
 /* Extension: the call above FUSED with fused_attention_ctx_pool.paged_min_max_pool of the

@@ -38,6 +38,7 @@ class KV4DecodeArgs(C.Structure):
         ("tokens_per_sub_chunk", c_i), ("hidden_dim_per_retrieval_token", c_i),
         ("quant_out", c_p), ("quant_scale", c_p), ("quant_sum", c_p),
         ("history_is_stable", c_i),
+        ("kv_scale_quant_orig", c_p), ("kv_scale_orig_quant", c_p),
     ]
 
 
@@ -51,6 +52,7 @@ class KV4PrefillArgs(C.Structure):
         ("num_retrieval_kv_heads", c_i), ("num_streaming_kv_heads", c_i),
         ("sink_token_num", c_i), ("local_token_num", c_i), ("sink_block_num", c_i), ("local_block_num", c_i),
         ("rotary_embedding_dim", c_i), ("rotary_base", c_f), ("rotary_scale", c_f),
+        ("kv_scale_orig_quant", c_p),
     ]
 
 

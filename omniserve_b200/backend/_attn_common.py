@@ -18,8 +18,10 @@ def _check_qkv(q, k, v):
 
 def single_query(q, k, v, r_tab, s_tab, flags, rank, dyn, lengths, tokens_per_block, n_r_heads, n_s_heads,
                  sink, local, sink_blk, local_blk, timestep, rot_dim, rot_base, rot_scale, force_split=0,
-                 tokens_per_sub_chunk=0, hidden_dim_per_retrieval_token=0, quant=None, history_is_stable=False):
-    """quant = (out_i8 [B, Hq*Dh], scale fp16 [B], sum fp16 [B] or None): also quantise the output row per token."""
+                 tokens_per_sub_chunk=0, hidden_dim_per_retrieval_token=0, quant=None, history_is_stable=False,
+                 kv8_scales=None):
+    """quant = (out_i8 [B, Hq*Dh], scale fp16 [B], sum fp16 [B] or None): also quantise the output row per token.
+    kv8_scales = (kv_scale_quant_orig, kv_scale_orig_quant) float32 [2] CUDA tensors: per-tensor INT8 pages."""
     _check_qkv(q, k, v)
     B, Hq, Dh = q.shape
     Hkv = k.shape[1]
@@ -48,6 +50,9 @@ def single_query(q, k, v, r_tab, s_tab, flags, rank, dyn, lengths, tokens_per_bl
     a.force_split = force_split
     a.tokens_per_sub_chunk, a.hidden_dim_per_retrieval_token = int(tokens_per_sub_chunk), int(hidden_dim_per_retrieval_token)
     a.history_is_stable = 1 if history_is_stable else 0
+    if kv8_scales is not None:
+        sqo, soq = (_kv8_scale(t) for t in kv8_scales)
+        a.kv_scale_quant_orig, a.kv_scale_orig_quant = L.ptr(sqo), L.ptr(soq)
     if quant is not None:
         qo, qs, qsum = quant
         L.require_cuda(qo, qs, qsum)
@@ -58,9 +63,17 @@ def single_query(q, k, v, r_tab, s_tab, flags, rank, dyn, lengths, tokens_per_bl
     return out
 
 
+def _kv8_scale(t):
+    """fused_attention_per_tensor/.../fused_attention.cpp: float32 tensor with the K and V scale."""
+    L.require_cuda(t)
+    if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < 2:
+        raise RuntimeError("kv_scale_quant_orig / kv_scale_orig_quant must be contiguous float32 tensors with 2 elements (K, V)")
+    return t
+
+
 def apply_rope_update_kv(qkv, seq_lens, padding_offset, r_tab, s_tab, flags, rank, head_num, kv_head_num, seq_len,
                          n_r_heads, n_s_heads, sink, local, sink_blk, local_blk, rot_dim, rot_base, rot_scale,
-                         pool_sub_chunk=0):
+                         pool_sub_chunk=0, kv8_scale_orig_quant=None):
     """pool_sub_chunk > 0 (extension): also write the kmax / kmin page statistics of the retrieval heads in the same pass
     (ob_kv4_apply_rope_update_kv_cache_pool)."""
     L.require_cuda(qkv, seq_lens, padding_offset)
@@ -79,6 +92,8 @@ def apply_rope_update_kv(qkv, seq_lens, padding_offset, r_tab, s_tab, flags, ran
     a.num_retrieval_kv_heads, a.num_streaming_kv_heads = n_r_heads, n_s_heads
     a.sink_token_num, a.local_token_num, a.sink_block_num, a.local_block_num = sink, local, sink_blk, local_blk
     a.rotary_embedding_dim, a.rotary_base, a.rotary_scale = int(rot_dim), float(rot_base), float(rot_scale)
+    if kv8_scale_orig_quant is not None:
+        a.kv_scale_orig_quant = L.ptr(_kv8_scale(kv8_scale_orig_quant))
     if pool_sub_chunk:
         L.check(L.lib().ob_kv4_apply_rope_update_kv_cache_pool(C.byref(a), int(pool_sub_chunk), L.stream()),
                 "apply_bias_rope_update_kv_cache + paged_min_max_pool (fused)")

@@ -187,6 +187,8 @@ int ob_kv4_single_query_attention(const ob_kv4_decode_args* x, void* stream) {
   a.hidden_dim_per_retrieval_token = x->hidden_dim_per_retrieval_token;
   a.q_out = reinterpret_cast<int8_t*>(x->quant_out); a.q_scale = HM(x->quant_scale); a.q_sum = HM(x->quant_sum);
   a.stable_history = x->history_is_stable;
+  if ((x->kv_scale_quant_orig == nullptr) != (x->kv_scale_orig_quant == nullptr)) return OB_ERR_ARG;
+  a.kv_scale_quant_orig = x->kv_scale_quant_orig; a.kv_scale_orig_quant = x->kv_scale_orig_quant;
   return kv4_decode_run(a, ST(stream));
 }
 
@@ -203,6 +205,7 @@ int ob_kv4_apply_rope_update_kv_cache(const ob_kv4_prefill_args* x, void* stream
   a.sink_blocks = x->sink_block_num; a.local_blocks = x->local_block_num;
   a.rotary_dim = x->rotary_embedding_dim; a.rotary_base = x->rotary_base;
   a.rotary_scale = x->rotary_scale != 0.f ? 1.0f / x->rotary_scale : 1.0f;
+  a.kv_scale_orig_quant = x->kv_scale_orig_quant;
   return kv4_prefill_write_run(a, ST(stream));
 }
 

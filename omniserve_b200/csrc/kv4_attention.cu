@@ -128,6 +128,8 @@ struct AttnParams {
   // precedes, pages older than the newest are >= 1 step old), so they may be read while that kernel is still draining.
   // 0 (default of the drop-in ops) = nothing is read before the grid dependency has resolved.
   int stable_history;
+  // per-tensor KV8 cache (fused_attention_per_tensor_*): device float[2] = (K, V) dequant / quant scales; null = KV4
+  const float* kv_scale_quant_orig; const float* kv_scale_orig_quant;
 };
 
 // invoke_quant(_fuse_sum) (fused_kernels.cu:57-142) of one attention-output row by the first 128 threads of the CTA,
@@ -219,6 +221,10 @@ OB_DEVICE void fused_quant_tail(const AttnParams& p, int b, int* flag, float* re
 // ------------------------------------------------------------------------------------------------
 constexpr int V2_STAGES = 4;
 constexpr int V2_STAGE_BYTES = 2 * 4096 + 4 * 128;
+// per-tensor KV8 pages (fused_attention_per_tensor_*, cache_engine.py:73-88): a (page, head) slice is 64 tokens x 128 int8 of
+// K and of V, no per-token scale rows
+constexpr int V8_STAGES = 3;
+constexpr int V8_STAGE_BYTES = 2 * 8192;
 constexpr int V2_THREADS = 160;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -279,16 +285,21 @@ struct Visits {
   }
 };
 
-__global__ void __launch_bounds__(V2_THREADS, 4)
+template <bool KV8>
+__global__ void __launch_bounds__(V2_THREADS, KV8 ? 3 : 4)
 kv4_decode_kernel(const AttnParams p, const int G) {
-  extern __shared__ __align__(128) uint8_t ring[];  // V2_STAGES * V2_STAGE_BYTES, reused for the final merge
+  constexpr int NSTAGE = KV8 ? V8_STAGES : V2_STAGES;
+  constexpr int STAGE_BYTES = KV8 ? V8_STAGE_BYTES : V2_STAGE_BYTES;
+  constexpr int ROW_BYTES = KV8 ? DH : DH / 2;          // bytes of one cached token of one head
+  constexpr int SLICE = TPB * ROW_BYTES;                 // bytes of one (page, head) slice of K or of V
+  extern __shared__ __align__(128) uint8_t ring[];  // NSTAGE * STAGE_BYTES, reused for the final merge
   __shared__ __align__(16) __half q_s[8][DH];
   __shared__ __align__(16) __half kv_new[2][DH];
   __shared__ float qsum_s[8], qbias_s[8], cur_logit_s[8];
   __shared__ float rope_cs[DH / 2], rope_sn[DH / 2];
   __shared__ int64_t kptr_s[32], vptr_s[32];
   __shared__ float ml_s[4][8][2];
-  __shared__ __align__(8) uint64_t full[V2_STAGES], empty[V2_STAGES];
+  __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE];
   __shared__ int flag_s;
   __shared__ float red_s[64];
 
@@ -327,7 +338,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
     sv.gap = tl - sv.n_valid;
     sv.sink_tok = p.sink_tok; sv.sink_blk = p.sink_blk; sv.local_blk = p.local_blk;
   }
-  sv.data_bytes = sv.hpool * TPB * (DH / 2);
+  sv.data_bytes = sv.hpool * SLICE;
   Visits vis;
   vis.init(sv, tl, p.dyn_pages);
   const int per_split = (vis.n + p.n_split - 1) / p.n_split;
@@ -336,7 +347,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
   const bool owns_current = (split == p.n_split - 1);
 
   if (tid == 0) {
-    for (int i = 0; i < V2_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
     mbar_fence_init();
   }
   __syncthreads();
@@ -371,15 +382,17 @@ kv4_decode_kernel(const AttnParams p, const int G) {
           mbar_wait(&empty[s], ph ^ 1);
           const uint8_t* kp = reinterpret_cast<const uint8_t*>(kptr_s[i]);
           const uint8_t* vp = reinterpret_cast<const uint8_t*>(vptr_s[i]);
-          uint8_t* st = ring + s * V2_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[s], V2_STAGE_BYTES);
-          bulk_g2s(st, kp + (size_t)sv.rank * 4096, 4096, &full[s]);
-          bulk_g2s(st + 4096, vp + (size_t)sv.rank * 4096, 4096, &full[s]);
-          bulk_g2s(st + 8192, kp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
-          bulk_g2s(st + 8192 + 128, kp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
-          bulk_g2s(st + 8192 + 256, vp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
-          bulk_g2s(st + 8192 + 384, vp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
-          if (++s == V2_STAGES) { s = 0; ph ^= 1; }
+          uint8_t* st = ring + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          bulk_g2s(st, kp + (size_t)sv.rank * SLICE, SLICE, &full[s]);
+          bulk_g2s(st + SLICE, vp + (size_t)sv.rank * SLICE, SLICE, &full[s]);
+          if (!KV8) {
+            bulk_g2s(st + 8192, kp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
+            bulk_g2s(st + 8192 + 128, kp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
+            bulk_g2s(st + 8192 + 256, vp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
+            bulk_g2s(st + 8192 + 384, vp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
+          }
+          if (++s == NSTAGE) { s = 0; ph ^= 1; }
         }
       }
       __syncwarp();
@@ -434,7 +447,9 @@ kv4_decode_kernel(const AttnParams p, const int G) {
         const int d = lane * 4 + i;
         const float qv = __half2float(q_s[h][d]);
         dot += qv * __half2float(kv_new[0][d]);
-        if (i & 1) {
+        if (KV8) {
+          bias += qv;          // int8 codes enter the MMAs as 1152 + code (1024 + (code ^ 0x80)): no per-dimension rescale
+        } else if (i & 1) {
           const __half qh = __float2half_rn(qv * 0.0625f);
           q_s[h][d] = qh;
           const float qe = __half2float(qh);
@@ -451,7 +466,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
         dot += __shfl_xor_sync(0xffffffffu, dot, m);
         bias += __shfl_xor_sync(0xffffffffu, bias, m);
       }
-      if (lane == 0) { qsum_s[h] = s; qbias_s[h] = 1024.f * bias; cur_logit_s[h] = dot * qk_scale; }
+      if (lane == 0) { qsum_s[h] = s; qbias_s[h] = (KV8 ? 1152.f : 1024.f) * bias; cur_logit_s[h] = dot * qk_scale; }
     }
     const bool writer = owns_current && ((G > 1) || group == 1 || (hq0 == hkv * group));
     if (writer && warp >= 2) {
@@ -464,8 +479,17 @@ kv4_decode_kernel(const AttnParams p, const int G) {
       __half x[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) x[i] = kv_new[which][lane * 4 + i];
-      __half* sc = reinterpret_cast<__half*>(page + sv.data_bytes) + sv.rank * TPB + slot;
-      quant_store_token(x, page + (size_t)sv.rank * TPB * (DH / 2) + slot * (DH / 2), sc, sc + sv.hpool * TPB, lane);
+      if (KV8) {
+        // per-tensor INT8: code = cvt.rni.sat.s8(x * scale_orig_quant) (common/...Utils.h:2041-2048); 128 B per token row
+        const float sq = p.kv_scale_orig_quant[which];
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w |= ((uint32_t)(uint8_t)f2i8_rni_sat(__half2float(x[i]) * sq)) << (8 * i);
+        reinterpret_cast<uint32_t*>(page + (size_t)sv.rank * SLICE + slot * ROW_BYTES)[lane] = w;
+      } else {
+        __half* sc = reinterpret_cast<__half*>(page + sv.data_bytes) + sv.rank * TPB + slot;
+        quant_store_token(x, page + (size_t)sv.rank * TPB * (DH / 2) + slot * (DH / 2), sc, sc + sv.hpool * TPB, lane);
+      }
       if (which == 0 && is_retrieval && p.sub_chunk > 0) {
         // LServe: fold the appended post-RoPE key into the kmax / kmin statistics of its sub-chunk, element-wise
         // against what the page holds (sparse_attention/...Template.hpp:1414-1429; fmaxf / fminf on fp16 values).
@@ -489,25 +513,58 @@ kv4_decode_kernel(const AttnParams p, const int G) {
     // ================================================================ compute warps
     const int g = lane >> 2, c = lane & 3;
     uint32_t qB[16];
+    if (KV8) {
+      // K-step s (16 dims) of the S^T MMAs: k-index 2c+i <-> dim 32c+4s+i, k-index 2c+8+i <-> dim 32c+4s+2+i (i = 0, 1): the four
+      // bytes a lane reads per token row and K-step are one 32-bit word (any bijection works as long as Q uses the same one)
 #pragma unroll
-    for (int w = 0; w < 4; ++w)
+      for (int ks = 0; ks < 8; ++ks) {
+        qB[2 * ks] = h2_as_u32(__halves2half2(q_s[g][c * 32 + 4 * ks], q_s[g][c * 32 + 4 * ks + 1]));
+        qB[2 * ks + 1] = h2_as_u32(__halves2half2(q_s[g][c * 32 + 4 * ks + 2], q_s[g][c * 32 + 4 * ks + 3]));
+      }
+    } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        qB[w * 4 + j] = h2_as_u32(__halves2half2(q_s[g][c * 32 + w * 8 + j], q_s[g][c * 32 + w * 8 + j + 4]));
+      for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          qB[w * 4 + j] = h2_as_u32(__halves2half2(q_s[g][c * 32 + w * 8 + j], q_s[g][c * 32 + w * 8 + j + 4]));
+    }
     const float qs0 = qsum_s[2 * c], qs1 = qsum_s[2 * c + 1];
     const float qb0 = qbias_s[2 * c], qb1 = qbias_s[2 * c + 1];
+    const float k_ts = KV8 ? p.kv_scale_quant_orig[0] : 1.f;   // per-tensor dequant scale of K
     const int base = warp * 16;
     const int tok_a = base + kappa(g), tok_b = base + kappa(g + 8);
-    const uint32_t ka_off = tok_a * 64 + c * 16, kb_off = tok_b * 64 + c * 16;
-    const uint32_t v_off0 = 4096 + (base + kappa(2 * c)) * 64 + g * 8, v_off1 = 4096 + (base + kappa(2 * c + 1)) * 64 + g * 8;
-    const uint32_t v_off2 = 4096 + (base + kappa(8 + 2 * c)) * 64 + g * 8, v_off3 = 4096 + (base + kappa(9 + 2 * c)) * 64 + g * 8;
+    const uint32_t ka_off = tok_a * ROW_BYTES + c * (ROW_BYTES / 4), kb_off = tok_b * ROW_BYTES + c * (ROW_BYTES / 4);
+    constexpr int VCH = ROW_BYTES / 8;     // bytes of the 16 dims [16g, 16g+16) of one token: 8 (nibbles) / 16 (int8)
+    const uint32_t v_off0 = SLICE + (base + kappa(2 * c)) * ROW_BYTES + g * VCH, v_off1 = SLICE + (base + kappa(2 * c + 1)) * ROW_BYTES + g * VCH;
+    const uint32_t v_off2 = SLICE + (base + kappa(8 + 2 * c)) * ROW_BYTES + g * VCH, v_off3 = SLICE + (base + kappa(9 + 2 * c)) * ROW_BYTES + g * VCH;
     int s = 0, ph = 0;
     for (int v = v0; v < v1; ++v) {
       const Visit vv = vis.get(v);
       mbar_wait(&full[s], ph);
       if (base < vv.hi && base + 16 > vv.lo) {
-        const uint8_t* st = ring + s * V2_STAGE_BYTES;
+        const uint8_t* st = ring + s * STAGE_BYTES;
         const __half* ksc = reinterpret_cast<const __half*>(st + 8192);
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+        uint4 W0, W1, W2, W3;              // V bytes of this lane's four tokens (KV8: 16 B each; KV4: the low 8 B are used)
+        if (KV8) {
+          // ---------------- S^T = (1152 + k8) . Q^T   (bias removed below); int8 -> exact fp16 1024 + (code ^ 0x80) with one prmt
+          const uint4 ka0 = *reinterpret_cast<const uint4*>(st + ka_off), ka1 = *reinterpret_cast<const uint4*>(st + ka_off + 16);
+          const uint4 kb0 = *reinterpret_cast<const uint4*>(st + kb_off), kb1 = *reinterpret_cast<const uint4*>(st + kb_off + 16);
+          W0 = *reinterpret_cast<const uint4*>(st + v_off0);
+          W1 = *reinterpret_cast<const uint4*>(st + v_off1);
+          W2 = *reinterpret_cast<const uint4*>(st + v_off2);
+          W3 = *reinterpret_cast<const uint4*>(st + v_off3);
+          const uint32_t kaw[8] = {ka0.x, ka0.y, ka0.z, ka0.w, ka1.x, ka1.y, ka1.z, ka1.w};
+          const uint32_t kbw[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t xa = kaw[ks] ^ 0x80808080u, xb = kbw[ks] ^ 0x80808080u;
+            const uint32_t a0 = __byte_perm(xa, 0x64646464u, 0x5140), a2 = __byte_perm(xa, 0x64646464u, 0x7362);
+            const uint32_t a1 = __byte_perm(xb, 0x64646464u, 0x5140), a3 = __byte_perm(xb, 0x64646464u, 0x7362);
+            if (ks & 1) mma16816(sb, a0, a1, a2, a3, qB[2 * ks], qB[2 * ks + 1]);
+            else mma16816(sa, a0, a1, a2, a3, qB[2 * ks], qB[2 * ks + 1]);
+          }
+        } else {
         // ---------------- S^T = (1024 + c n_K) . Q'^T     (bias removed below)
         const uint4 ka = *reinterpret_cast<const uint4*>(st + ka_off);
         const uint4 kb = *reinterpret_cast<const uint4*>(st + kb_off);
@@ -515,7 +572,8 @@ kv4_decode_kernel(const AttnParams p, const int G) {
         const uint2 w1 = *reinterpret_cast<const uint2*>(st + v_off1);
         const uint2 w2 = *reinterpret_cast<const uint2*>(st + v_off2);
         const uint2 w3 = *reinterpret_cast<const uint2*>(st + v_off3);
-        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+        W0 = make_uint4(w0.x, w0.y, 0, 0); W1 = make_uint4(w1.x, w1.y, 0, 0);
+        W2 = make_uint4(w2.x, w2.y, 0, 0); W3 = make_uint4(w3.x, w3.y, 0, 0);
         const uint32_t kaw[4] = {ka.x, ka.y, ka.z, ka.w}, kbw[4] = {kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
@@ -533,15 +591,24 @@ kv4_decode_kernel(const AttnParams p, const int G) {
           mma16816(sa, a0, b0, a1, b1, qB[4 * w], qB[4 * w + 1]);
           mma16816(sb, a2, b2, a3, b3, qB[4 * w + 2], qB[4 * w + 3]);
         }
+        }
         const bool full_page = (vv.lo == 0) & (vv.hi == TPB);
         const bool va = full_page || (tok_a >= vv.lo && tok_a < vv.hi);
         const bool vb = full_page || (tok_b >= vv.lo && tok_b < vv.hi);
-        const float ksa = __half2float(ksc[tok_a]), kza = __half2float(ksc[64 + tok_a]);
-        const float ksb = __half2float(ksc[tok_b]), kzb = __half2float(ksc[64 + tok_b]);
-        const float la0 = va ? ksa * ((sa[0] + sb[0]) - qb0 - kza * qs0) * qk_scale : -INFINITY;
-        const float la1 = va ? ksa * ((sa[1] + sb[1]) - qb1 - kza * qs1) * qk_scale : -INFINITY;
-        const float lb0 = vb ? ksb * ((sa[2] + sb[2]) - qb0 - kzb * qs0) * qk_scale : -INFINITY;
-        const float lb1 = vb ? ksb * ((sa[3] + sb[3]) - qb1 - kzb * qs1) * qk_scale : -INFINITY;
+        float la0, la1, lb0, lb1;
+        if (KV8) {
+          la0 = va ? k_ts * ((sa[0] + sb[0]) - qb0) * qk_scale : -INFINITY;
+          la1 = va ? k_ts * ((sa[1] + sb[1]) - qb1) * qk_scale : -INFINITY;
+          lb0 = vb ? k_ts * ((sa[2] + sb[2]) - qb0) * qk_scale : -INFINITY;
+          lb1 = vb ? k_ts * ((sa[3] + sb[3]) - qb1) * qk_scale : -INFINITY;
+        } else {
+          const float ksa = __half2float(ksc[tok_a]), kza = __half2float(ksc[64 + tok_a]);
+          const float ksb = __half2float(ksc[tok_b]), kzb = __half2float(ksc[64 + tok_b]);
+          la0 = va ? ksa * ((sa[0] + sb[0]) - qb0 - kza * qs0) * qk_scale : -INFINITY;
+          la1 = va ? ksa * ((sa[1] + sb[1]) - qb1 - kza * qs1) * qk_scale : -INFINITY;
+          lb0 = vb ? ksb * ((sa[2] + sb[2]) - qb0 - kzb * qs0) * qk_scale : -INFINITY;
+          lb1 = vb ? ksb * ((sa[3] + sb[3]) - qb1 - kzb * qs1) * qk_scale : -INFINITY;
+        }
         // ---------------- online softmax over the 16 tokens (lanes with equal c share the heads 2c, 2c+1)
         float x0 = fmaxf(la0, lb0), x1 = fmaxf(la1, lb1);
 #pragma unroll
@@ -560,8 +627,13 @@ kv4_decode_kernel(const AttnParams p, const int G) {
         const float pa0 = ex2(la0 - m0), pa1 = ex2(la1 - m1), pb0 = ex2(lb0 - m0), pb1 = ex2(lb1 - m1);
         l0 += pa0 + pb0;
         l1 += pa1 + pb1;
-        const float vsa = va ? __half2float(ksc[128 + tok_a]) : 0.f, vza = va ? __half2float(ksc[192 + tok_a]) : 0.f;
-        const float vsb = vb ? __half2float(ksc[128 + tok_b]) : 0.f, vzb = vb ? __half2float(ksc[192 + tok_b]) : 0.f;
+        float vsa, vza, vsb, vzb;
+        if (KV8) {   // per-tensor V scale is applied once at the end; masked tokens contribute nothing
+          vsa = va ? 1.f : 0.f; vsb = vb ? 1.f : 0.f; vza = 0.f; vzb = 0.f;
+        } else {
+          vsa = va ? __half2float(ksc[128 + tok_a]) : 0.f; vza = va ? __half2float(ksc[192 + tok_a]) : 0.f;
+          vsb = vb ? __half2float(ksc[128 + tok_b]) : 0.f; vzb = vb ? __half2float(ksc[192 + tok_b]) : 0.f;
+        }
         const __half2 ha = __floats2half2_rn(pa0 * vsa, pa1 * vsa), hb = __floats2half2_rn(pb0 * vsb, pb1 * vsb);
         const float2 fa = __half22float2(ha), fb = __half22float2(hb);  // the values the MMA will really use
         sp0 += fa.x + fb.x;
@@ -570,11 +642,25 @@ kv4_decode_kernel(const AttnParams p, const int G) {
         corr1 += fa.y * vza + fb.y * vzb;
         const uint32_t pb_lo = movmatrix_trans(h2_as_u32(ha));
         const uint32_t pb_hi = movmatrix_trans(h2_as_u32(hb));
+        if (KV8) {
+          // ---------------- O^T += (1152 + v8)^T . P^T : MMA j, row g <-> dim 16g+2j, row g+8 <-> dim 16g+2j+1; k <-> this lane's 4 tokens
+          const uint32_t w0a[4] = {W0.x, W0.y, W0.z, W0.w}, w1a[4] = {W1.x, W1.y, W1.z, W1.w};
+          const uint32_t w2a[4] = {W2.x, W2.y, W2.z, W2.w}, w3a[4] = {W3.x, W3.y, W3.z, W3.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t sel = (j & 1) ? 0x7362u : 0x5140u;   // bytes (2, 6, 3, 7) or (0, 4, 1, 5): dims 2j, 2j+1 of both tokens
+            const uint32_t g01 = __byte_perm(w0a[j >> 1], w1a[j >> 1], sel) ^ 0x80808080u;   // [t0 d, t1 d, t0 d+1, t1 d+1]
+            const uint32_t g23 = __byte_perm(w2a[j >> 1], w3a[j >> 1], sel) ^ 0x80808080u;
+            const uint32_t t0 = __byte_perm(g01, 0x64646464u, 0x5140), t1 = __byte_perm(g01, 0x64646464u, 0x7362);
+            const uint32_t t2 = __byte_perm(g23, 0x64646464u, 0x5140), t3 = __byte_perm(g23, 0x64646464u, 0x7362);
+            mma16816(acc[j], t0, t1, t2, t3, pb_lo, pb_hi);
+          }
+        } else {
         // ---------------- O^T += (1024 + c n_V)^T . P'^T
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t A = j < 4 ? w0.x : w0.y, B = j < 4 ? w1.x : w1.y, Cw = j < 4 ? w2.x : w2.y,
-                         D = j < 4 ? w3.x : w3.y;
+          const uint32_t A = j < 4 ? W0.x : W0.y, B = j < 4 ? W1.x : W1.y, Cw = j < 4 ? W2.x : W2.y,
+                         D = j < 4 ? W3.x : W3.y;
           const uint32_t sel = (uint32_t)(j & 3) | ((uint32_t)(4 + (j & 3)) << 8);
           const uint32_t u01 = __byte_perm(A, B, sel), u23 = __byte_perm(Cw, D, sel);
           uint32_t t0, t1, t2, t3;
@@ -584,10 +670,11 @@ kv4_decode_kernel(const AttnParams p, const int G) {
           asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(t3) : "r"(u23));
           mma16816(acc[j], t0, t1, t2, t3, pb_lo, pb_hi);
         }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
-      if (++s == V2_STAGES) { s = 0; ph ^= 1; }
+      if (++s == NSTAGE) { s = 0; ph ^= 1; }
     }
     // per-warp totals: l, sp and corr are per-thread partials over the rows g of equal c
 #pragma unroll
@@ -609,8 +696,14 @@ kv4_decode_kernel(const AttnParams p, const int G) {
       // acc[j] = O^T[dims 16g+2j (rows g), 16g+2j+1 (rows g+8)][heads 2c, 2c+1]
       float* o0 = obuf + ((warp * 8 + 2 * c) * DH) + 16 * g + 2 * j;
       float* o1 = o0 + DH;
-      o0[0] = (acc[j][0] - 1024.f * sp0) - corr0; o0[1] = (acc[j][2] - 1024.f * sp0) * 0.0625f - corr0;
-      o1[0] = (acc[j][1] - 1024.f * sp1) - corr1; o1[1] = (acc[j][3] - 1024.f * sp1) * 0.0625f - corr1;
+      if (KV8) {
+        const float v_ts = p.kv_scale_quant_orig[1];      // per-tensor dequant scale of V
+        o0[0] = (acc[j][0] - 1152.f * sp0) * v_ts; o0[1] = (acc[j][2] - 1152.f * sp0) * v_ts;
+        o1[0] = (acc[j][1] - 1152.f * sp1) * v_ts; o1[1] = (acc[j][3] - 1152.f * sp1) * v_ts;
+      } else {
+        o0[0] = (acc[j][0] - 1024.f * sp0) - corr0; o0[1] = (acc[j][2] - 1024.f * sp0) * 0.0625f - corr0;
+        o1[0] = (acc[j][1] - 1024.f * sp1) - corr1; o1[1] = (acc[j][3] - 1024.f * sp1) * 0.0625f - corr1;
+      }
     }
     if (g == 0) {
       ml_s[warp][2 * c][0] = m0; ml_s[warp][2 * c][1] = l0;
@@ -686,7 +779,17 @@ struct PrefillParams {
   int T, Hq, Hkv, r_hpool, s_hpool;
   int sink_tok, local_tok, sink_blk, local_blk;
   int rotary_dim; float rope_base, rope_scale;
+  const float* kv_scale_orig_quant;   // non-null: per-tensor INT8 pages (K scale, V scale), 128 B per token row
 };
+
+// per-tensor INT8 row of one (token, kv head): lane l holds dims 2l, 2l+1, 64+2l, 65+2l (per_tensor_common/update_kv_cache.cu:27-,
+// store_8bits_kv_cache_vec: code = cvt.rni.sat.s8(x * scale_orig_quant))
+OB_DEVICE void quant8_store_pairs(const float (&x)[4], uint8_t* row, float sq, int lane) {
+  const uint16_t lo = (uint16_t)((uint8_t)f2i8_rni_sat(x[0] * sq) | ((uint32_t)(uint8_t)f2i8_rni_sat(x[1] * sq) << 8));
+  const uint16_t hi = (uint16_t)((uint8_t)f2i8_rni_sat(x[2] * sq) | ((uint32_t)(uint8_t)f2i8_rni_sat(x[3] * sq) << 8));
+  reinterpret_cast<uint16_t*>(row)[lane] = lo;
+  reinterpret_cast<uint16_t*>(row + 64)[lane] = hi;
+}
 
 OB_DEVICE void quant_store_pairs(const float (&x)[4], uint8_t* row, __half* scale_ptr, __half* zero_ptr, int lane) {
   float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
@@ -780,6 +883,10 @@ __global__ void __launch_bounds__(256) kv4_prefill_write_kernel(const PrefillPar
       }
       uint8_t* page = reinterpret_cast<uint8_t*>(tab[tabidx]);
       const int slot = pos & 63;
+      if (p.kv_scale_orig_quant) {
+        quant8_store_pairs(x, page + (size_t)rank * TPB * DH + slot * DH, p.kv_scale_orig_quant[is_v ? 1 : 0], lane);
+        continue;
+      }
       const int data_bytes = hpool * TPB * (DH / 2);
       __half* sc = reinterpret_cast<__half*>(page + data_bytes) + rank * TPB + slot;
       quant_store_pairs(x, page + (size_t)rank * TPB * (DH / 2) + slot * (DH / 2), sc, sc + hpool * TPB, lane);
@@ -1015,7 +1122,19 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
     p.part_o = ws.part_o; p.part_ml = ws.part_ml; p.counters = ws.cnt;
   }
   dim3 grid(n_split, ctas_y, a.B);
-  return launch_pdl(kv4_decode_kernel, grid, dim3(V2_THREADS), (size_t)(V2_STAGES * V2_STAGE_BYTES), st, p, G) == cudaSuccess
+  if (a.kv_scale_quant_orig) {
+    if (!a.kv_scale_orig_quant) return OB_ERR_ARG;
+    p.kv_scale_quant_orig = a.kv_scale_quant_orig; p.kv_scale_orig_quant = a.kv_scale_orig_quant;
+    static bool attr_done[ATT_MAX_DEV] = {};
+    if (!attr_done[dev]) {
+      if (cudaFuncSetAttribute(kv4_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V8_STAGES * V8_STAGE_BYTES) != cudaSuccess)
+        return OB_ERR_CUDA;
+      attr_done[dev] = true;
+    }
+    return launch_pdl(kv4_decode_kernel<true>, grid, dim3(V2_THREADS), (size_t)(V8_STAGES * V8_STAGE_BYTES), st, p, G) == cudaSuccess
+               ? 0 : OB_ERR_CUDA;
+  }
+  return launch_pdl(kv4_decode_kernel<false>, grid, dim3(V2_THREADS), (size_t)(V2_STAGES * V2_STAGE_BYTES), st, p, G) == cudaSuccess
              ? 0 : OB_ERR_CUDA;
 }
 
@@ -1035,6 +1154,7 @@ int kv4_prefill_write_run(const KV4PrefillArgs& a, cudaStream_t st) {
   p.sink_tok = a.sink_tokens; p.local_tok = a.local_tokens; p.sink_blk = a.sink_blocks;
   p.local_blk = a.local_blocks > 0 ? a.local_blocks : 1;
   p.rotary_dim = a.rotary_dim; p.rope_base = a.rotary_base; p.rope_scale = a.rotary_scale;
+  p.kv_scale_orig_quant = a.kv_scale_orig_quant;
   const int blocks = (int)std::min<long long>(((long long)a.T + 3) / 4, 148LL * 8);
   return launch_pdl(kv4_prefill_write_kernel, dim3(blocks), dim3(256), 0, st, p) == cudaSuccess ? 0 : OB_ERR_CUDA;
 }
@@ -1048,6 +1168,7 @@ int padding_offsets_run(int* out, const int* cu_seqlens, int B, int max_seq_len,
 int kv4_prefill_write_pool_run(const KV4PrefillArgs& a, int tokens_per_sub_chunk, cudaStream_t st) {
   if (a.T <= 0) return 0;
   if (a.rotary_dim != DH || tokens_per_sub_chunk != FP_SUB || a.num_retrieval_kv_heads > FP_MAX_HR || a.B <= 0) return OB_ERR_SHAPE;
+  if (a.kv_scale_orig_quant) return OB_ERR_ARG;   // the fused statistics pass is KV4-only
   PrefillParams p{};
   p.qkv = a.qkv; p.seq_lens = a.seq_lens; p.padding_offset = a.padding_offset; p.max_seq_len = a.max_seq_len;
   p.r_tab = a.retrieval_kv_pointers; p.s_tab = a.streaming_kv_pointers;

@@ -29,6 +29,8 @@ struct KV4DecodeArgs {
   int tokens_per_sub_chunk = 0;                        // > 0: fold the appended key into the page's kmax / kmin
   int hidden_dim_per_retrieval_token = 0;
   int stable_history = 0;                              // see AttnParams::stable_history
+  const float* kv_scale_quant_orig = nullptr;          // non-null: per-tensor KV8 pages (device float[2]: K, V dequant scales)
+  const float* kv_scale_orig_quant = nullptr;          //           and the quant scales used for the appended token
 };
 
 int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st);
@@ -44,6 +46,7 @@ struct KV4PrefillArgs {
   int num_retrieval_kv_heads, num_streaming_kv_heads;
   int sink_tokens, local_tokens, sink_blocks, local_blocks;
   int rotary_dim; float rotary_base; float rotary_scale;
+  const float* kv_scale_orig_quant = nullptr;          // non-null: per-tensor KV8 pages (device float[2])
 };
 int kv4_prefill_write_run(const KV4PrefillArgs& a, cudaStream_t st);
 // fused: the same page writes + the kmax / kmin statistics of every 16-token sub-chunk of the retrieval heads

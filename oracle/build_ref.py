@@ -66,6 +66,12 @@ MODULES = {
         f"{FA}/fused_attention_fine_grained/fine_grained_common/update_kv_cache.cu",
         f"{FA}/common/input_metadata_helper.cu",
     ],
+    "fused_attention_per_tensor_dense": [
+        f"{FA}/fused_attention_per_tensor/dense_attention/fused_attention.cpp",
+        f"{FA}/fused_attention_per_tensor/dense_attention/decoderMaskedMultiheadAttention.cu",
+        f"{FA}/fused_attention_per_tensor/per_tensor_common/update_kv_cache.cu",
+        f"{FA}/common/input_metadata_helper.cu",
+    ],
     "fused_attention_selector": [
         f"{FA}/sparse_utils/KVPageSelector/fused_kv_page_selector.cpp",
         f"{FA}/sparse_utils/KVPageSelector/KVPageSelector.cu",
