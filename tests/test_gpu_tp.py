@@ -29,7 +29,7 @@ def test_tensor_parallel_exact_partials_exchange_and_end_to_end(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "tp_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    tail = (r.stdout + r.stderr)[-4000:]
+    tail = r.stdout[-3000:] + "\n--- stderr (tail) ---\n" + r.stderr[-2500:]
     print(tail)
     assert r.returncode == 0, tail
     assert f"tp{world}:" in r.stdout and "OK" in r.stdout
