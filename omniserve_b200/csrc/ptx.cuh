@@ -279,6 +279,17 @@ OB_DEVICE uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t cta_rank) {
 OB_DEVICE void st_shared_cluster_u32(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
 }
+OB_DEVICE int32_t ld_shared_cluster_s32(uint32_t cluster_addr) {
+  int32_t v;
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+// execution barrier only (no memory ordering): e.g. "nobody exits while a peer may still read its shared memory", when the
+// arriving thread's own remote loads have already returned (their values were consumed)
+OB_DEVICE void cluster_barrier_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 OB_DEVICE void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -39,6 +39,9 @@ constexpr int ACC_COLS = 64;
 #define OB_DEC_KPS 2
 #endif
 constexpr int KPS = OB_DEC_KPS;
+#ifndef OB_DEC_CLUSTER_DEFAULT
+#define OB_DEC_CLUSTER_DEFAULT false
+#endif
 constexpr int AB_STAGES = (TMEM_COLS - ACC_COLS) / (A_COLS * KPS);   // 3 steps: TMEM A ring == activation ring depth
 
 template <int BN>
@@ -67,6 +70,7 @@ struct Params {
   int M, N, K, ldc;
   int n_tiles, kb_per_tile, units_per_cta;
   int n_tiles_e;      // grouped mode: n-tiles per expert (n_tiles = groups * n_tiles_e)
+  int cluster_s;      // > 1: the cluster_s CTAs of a cluster are the K-slices of ONE tile; split-K reduced over DSMEM
   long long* dbg_t;   // -DOB_DEC_TIMING builds only (tools/dec_waits.py): [grid][32] globaltimer stamps
 };
 
@@ -117,6 +121,31 @@ OB_DEVICE void red_add_s32(int32_t* addr, int32_t v) {
   asm volatile("red.global.add.s32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
 OB_DEVICE void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the eight unpack / epilogue warps
+
+// Cluster split-K: the S CTAs of a cluster hold the INT32 partial tiles of the same output tile in their own shared memory
+// (layout [token column][128 rows]).  CTA `rank` owns BN / S token columns: thread (row = et & 127, h = et >> 7) reads the
+// partials of its columns from all S CTAs over distributed shared memory -- BN / 2 independent 4-byte loads, issued back to
+// back, 128 B per warp -- and returns the exact INT32 sums of columns rank * BN / S + h + 2 i in sum[i].
+template <int BN, int S>
+OB_DEVICE void cluster_reduce_cols(uint32_t stage_u32, uint32_t rank, int row, int h, int (&sum)[BN / 2]) {
+  constexpr int COLS = BN / S;          // columns owned by a CTA
+  constexpr int NI = COLS / 2;          // columns per thread
+  static_assert(COLS >= 2 && (COLS % 2) == 0, "two column phases per CTA");
+  int v[NI][S];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const uint32_t local = stage_u32 + (uint32_t)(((rank * COLS + h + 2 * i) * BM + row) * 4);
+#pragma unroll
+    for (int pr = 0; pr < S; ++pr) v[i][pr] = ld_shared_cluster_s32(mapa_shared(local, (uint32_t)pr));
+  }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    int a = 0;
+#pragma unroll
+    for (int pr = 0; pr < S; ++pr) a += v[i][pr];
+    sum[i] = a;
+  }
+}
 
 template <int BN, bool PER_GROUP, bool MOE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
@@ -383,6 +412,10 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
             else o = __fmaf_rn(-wsz, sTok[BN + m], (ps * wsc) * sTok[m]);
             if (n_ok && m < m_rows) p.out[(size_t)(row0 + m) * p.ldc + n_row] = __float2half_rn(o);
           }
+        } else if (!MOE && p.cluster_s > 1) {
+          // cluster split-K: park the partial in this CTA's (fully consumed) packed-weight ring, [column][row]
+#pragma unroll
+          for (int j = 0; j < CH; ++j) reinterpret_cast<int32_t*>(sW)[(c0 + j) * BM + q * 32 + lane] = (int)r[j];
         } else {
 #pragma unroll
           for (int j = 0; j < CH; ++j) red_add_s32(slot + (c0 + j) * BM + q * 32 + lane, (int)r[j]);
@@ -391,7 +424,36 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);    // MMAs of the next segment may overwrite the accumulator
-      if (!full_tile) {
+      if (!MOE && !full_tile && p.cluster_s > 1) {
+        // ---- exact INT32 split-K inside the cluster, over distributed shared memory: no L2 atomics, no arrival counter,
+        // no read-back by a "last" CTA -- every CTA finalises its own token columns (profiles/r2_dec_timeline.log: the
+        // L2 path costs 4-6 us of dependent round trips per split GEMM).
+        cluster_barrier();                       // all partials of the tile are in place (release / acquire, cluster scope)
+        const uint32_t rank = cluster_ctarank();
+        const int row = et & 127, h = et >> 7;
+        int sum[BN / 2];
+        int ncol = 0;
+        const uint32_t stage_u32 = smem_u32(sW);
+        switch (p.cluster_s) {
+          case 8: cluster_reduce_cols<BN, 8>(stage_u32, rank, row, h, sum); ncol = BN / 16; break;
+          case 4: cluster_reduce_cols<BN, 4>(stage_u32, rank, row, h, sum); ncol = BN / 8; break;
+          default: cluster_reduce_cols<BN, 2>(stage_u32, rank, row, h, sum); ncol = BN / 4; break;
+        }
+        const int col0 = (int)rank * (BN / p.cluster_s) + h;
+#pragma unroll
+        for (int i = 0; i < BN / 4; ++i) {
+          if (i < ncol) {
+            const int m = col0 + 2 * i;
+            const float ps = __int2float_rn(sum[i]);
+            float o;
+            if (PER_GROUP) o = ps * (wsc * sTok[m]);
+            else o = __fmaf_rn(-wsz, sTok[BN + m], (ps * wsc) * sTok[m]);
+            if (n_ok && m < m_rows) p.out[(size_t)(row0 + m) * p.ldc + n_row] = __float2half_rn(o);
+          }
+        }
+        cluster_barrier_relaxed();               // nobody leaves while a peer may still read its shared memory (the remote
+                                                 // loads of this thread have returned: their sums were just stored)
+      } else if (!full_tile) {
         // exact INT32 split-K: every contributor's reds must be performed before its arrival is counted
         const int last_cta = (int)(((long long)(sg.tile + 1) * p.kb_per_tile - 1) / p.units_per_cta);
         const int contributors = last_cta - first_cta + 1;
@@ -430,6 +492,11 @@ w4a8_gemm_decode_kernel(const __grid_constant__ CUtensorMap act_map, const __gri
     }
   }
 
+  if (!MOE && p.cluster_s > 1 && warp < 4) {   // producers / MMA / idle warp: the epilogue's two cluster barriers
+    __syncwarp();
+    cluster_barrier();
+    cluster_barrier_relaxed();
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -461,7 +528,33 @@ static int launch(const CUtensorMap& amap, const CUtensorMap& wmap, const Params
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL) != cudaSuccess) return OB_ERR_CUDA;
     attr_done[dev] = true;
   }
-  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, amap, wmap, p, NoMoe{}) == cudaSuccess ? 0 : OB_ERR_CUDA;
+  const unsigned cluster = p.cluster_s > 1 ? (unsigned)p.cluster_s : 1u;
+  return launch_pdl_cluster(kern, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_TOTAL, st, cluster, amap, wmap, p, NoMoe{}) == cudaSuccess
+             ? 0 : OB_ERR_CUDA;
+}
+
+// Can clusters of `s` CTAs of this kernel be co-scheduled at all on this device (two ~100 KB CTAs per SM, GPC sizes)?
+// Queried once per (device, BN, per_group, s); never during stream capture problems: the query launches nothing.
+template <int BN, bool PG>
+static bool cluster_ok(int dev, int s) {
+  static int ok[16][9] = {};   // 0 = unknown, 1 = yes, -1 = no
+  if (s < 2 || s > 8) return false;
+  if (!ok[dev][s]) {
+    using C = Cfg<BN>;
+    auto kern = w4a8_gemm_decode_kernel<BN, PG, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(s * 8); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_TOTAL;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = s; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess) cudaGetLastError();
+    ok[dev][s] = (e == cudaSuccess && n >= 1) ? 1 : -1;
+  }
+  return ok[dev][s] > 0;
 }
 
 }  // namespace dec
@@ -474,20 +567,28 @@ static int launch(const CUtensorMap& amap, const CUtensorMap& wmap, const Params
 //     ~0.01 us per contributing CTA of L2 atomic traffic -- so a whole 32-K-block tile per CTA (6.4 us) beats an 8-way
 //     split of it, and splitting only pays for long K (down_proj) or very few tiles;
 //   * ranges that straddle tile boundaries add a second epilogue and an uneven finish (~3 us).
-static int choose_upc(int n_tiles, int KB, int sms, int ctas_per_sm, int BN) {
+static bool cluster_split(int KB, int upc) {   // an aligned 2 / 4 / 8-way split: the K-slices of a tile form one cluster
+  if (upc >= KB || KB % upc) return false;
+  const int s = KB / upc;
+  return s == 2 || s == 4 || s == 8;
+}
+
+static int choose_upc(int n_tiles, int KB, int sms, int ctas_per_sm, int BN, bool use_cluster) {
   (void)BN;
   const long long units = (long long)n_tiles * KB;
   const int max_ctas = sms * ctas_per_sm;
   const int lo = (int)((units + max_ctas - 1) / max_ctas);
   if (lo >= KB) return KB * ((lo + KB - 1) / KB);   // at least a tile per CTA: whole tiles, no split
-  const float T_KB = 0.2f, T_FULL = 0.3f, T_SPLIT = 5.0f, T_CTA = 0.01f, T_UNALIGNED = 3.0f;
+  const float T_KB = 0.2f, T_FULL = 0.3f, T_SPLIT = 5.0f, T_SPLIT_CL = 1.5f, T_CTA = 0.01f, T_UNALIGNED = 3.0f;
   int best = KB;
   float best_cost = 1e30f;
   for (int upc = lo; upc <= KB; ++upc) {
     const long long n_ctas = (units + upc - 1) / upc;
     const int per_sm = (int)((n_ctas + sms - 1) / sms);
     float cost = per_sm * upc * T_KB;
-    cost += (upc < KB) ? (T_SPLIT + n_ctas * T_CTA) : T_FULL;
+    if (upc >= KB) cost += T_FULL;
+    else if (use_cluster && cluster_split(KB, upc)) cost += T_SPLIT_CL;      // reduced over DSMEM inside the cluster
+    else cost += T_SPLIT + n_ctas * T_CTA;
     if (KB % upc) cost += T_UNALIGNED;
     if (cost < best_cost - 1e-6f) { best_cost = cost; best = upc; }
   }
@@ -526,8 +627,22 @@ int w4a8_gemm_decode_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st)
   static const int ctas_per_sm = [] { const char* e = getenv("OB_GEMM_DEC_CTAS_PER_SM"); return e ? std::max(1, std::min(2, atoi(e))) : 2; }();
   int max_ctas = a.force_ctas > 0 ? std::min(a.force_ctas, 2 * sms) : ctas_per_sm * sms;
   const long long units = (long long)p.n_tiles * p.kb_per_tile;
-  p.units_per_cta = a.force_ctas > 0 ? (int)((units + max_ctas - 1) / max_ctas) : choose_upc(p.n_tiles, p.kb_per_tile, sms, ctas_per_sm, BN);
+  // split-K over distributed shared memory (cluster = the K-slices of one tile): OB_GEMM_DEC_CLUSTER=0 falls back to the L2 path
+  static const bool use_cluster = [] { const char* e = getenv("OB_GEMM_DEC_CLUSTER"); return e ? atoi(e) != 0 : OB_DEC_CLUSTER_DEFAULT; }();
+  p.units_per_cta = a.force_ctas > 0 ? (int)((units + max_ctas - 1) / max_ctas)
+                                     : choose_upc(p.n_tiles, p.kb_per_tile, sms, ctas_per_sm, BN, use_cluster);
   const int grid = (int)((units + p.units_per_cta - 1) / p.units_per_cta);
+  p.cluster_s = 0;
+  if (use_cluster && cluster_split(p.kb_per_tile, p.units_per_cta)) {
+    const int s = p.kb_per_tile / p.units_per_cta;
+    bool ok = false;
+    switch (BN) {
+      case 16: ok = per_group ? cluster_ok<16, true>(dev, s) : cluster_ok<16, false>(dev, s); break;
+      case 32: ok = per_group ? cluster_ok<32, true>(dev, s) : cluster_ok<32, false>(dev, s); break;
+      default: ok = per_group ? cluster_ok<64, true>(dev, s) : cluster_ok<64, false>(dev, s); break;
+    }
+    if (ok && grid == p.n_tiles * s) p.cluster_s = s;
+  }
   CUtensorMap amap, wmap;
   if (int e = make_act_map(&amap, a.in_feats, a.M, a.K, BN)) return e;
   if (int e = make_w_map(&wmap, a.qweight, a.N, a.K, false)) return e;

@@ -1,0 +1,64 @@
+"""Run by tests/test_gpu_gemm.py::test_decode_split_k_reduction_paths in a fresh process per value of OB_GEMM_DEC_CLUSTER (the
+library reads it once): decode-kernel GEMMs whose tiles are split 2 / 4 / 8 ways along K, against the oracle, with unit scales so
+that the fp16 outputs ARE the INT32 accumulators (|acc| <= 2048) -- integer equality, no tolerance.  Prints OK."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from omniserve_b200 import _lib as L  # noqa: E402
+from oracle import w4a8 as ow  # noqa: E402
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def case(M, N, K, ctas, per_group, seed):
+    rng = np.random.default_rng(seed)
+    q = rng.integers(0, 16, (N, K), dtype=np.uint8)
+    a = rng.integers(-1, 2, (M, K), dtype=np.int8)               # |acc| <= 15 K / ... stays far below 2048 for K <= 1024
+    a[rng.random((M, K)) < 0.7] = 0
+    qw = ow.pack_w4(q)
+    s1 = np.ones(N, np.float16)
+    sa = np.ones(M, np.float16)
+    out = torch.full((M, N), float("nan"), dtype=torch.float16, device="cuda")
+    if per_group:
+        ng = K // 128
+        s2 = ow.pack_s2(np.ones((N, ng), np.int64)).astype(np.int8)
+        z2 = ow.pack_s2(np.zeros((N, ng), np.int64)).astype(np.int8)
+        code = L.lib().ob_w4a8_gemm_ex(1, L.ptr(t(a)), L.ptr(t(qw)), L.ptr(t(z2)), L.ptr(t(s2)), L.ptr(t(s1)), L.ptr(t(sa)), 0, 0,
+                                       L.ptr(out), M, N, K, N, 0, 3, ctas, L.stream())
+    else:
+        szs = np.zeros(N, np.float16)
+        ssum = np.zeros(M, np.float16)
+        code = L.lib().ob_w4a8_gemm_ex(0, L.ptr(t(a)), L.ptr(t(qw)), 0, 0, L.ptr(t(s1)), L.ptr(t(sa)), L.ptr(t(szs)), L.ptr(t(ssum)),
+                                       L.ptr(out), M, N, K, N, 0, 3, ctas, L.stream())
+    torch.cuda.synchronize()
+    assert code == 0, code
+    want = a.astype(np.int64) @ q.astype(np.int64).T
+    assert np.abs(want).max() <= 2048
+    got = out.cpu().numpy().astype(np.float64)
+    assert np.array_equal(got, want.astype(np.float64)), (M, N, K, ctas, per_group, np.abs(got - want).max())
+
+
+def main():
+    n = 0
+    for per_group in (False, True):
+        for M in (7, 16, 32, 64):
+            for N, K, tiles in ((256, 1024, 2), (384, 2048, 3)):
+                kb = K // 128
+                for s in (2, 4, 8):
+                    for rep in range(2):                      # twice: the L2 path must leave its workspace clean
+                        case(M, N, K, tiles * s, per_group, seed=1000 * M + s + rep)
+                        n += 1
+                case(M, N, K, tiles, per_group, seed=M)        # whole tiles
+                case(M, N, K, tiles * kb, per_group, seed=M)   # one K-block per CTA (kb-way split: never a cluster for kb = 16)
+    print(f"OK {n} split cases, OB_GEMM_DEC_CLUSTER={os.environ.get('OB_GEMM_DEC_CLUSTER')}")
+
+
+if __name__ == "__main__":
+    main()

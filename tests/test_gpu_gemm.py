@@ -54,6 +54,20 @@ def test_llama3_8b_decode_shapes_bs64(N, K):
     assert run(64, N, K, False, seed=N + K) > 0.999
 
 
+@pytest.mark.parametrize("cluster", ["0", "1"])
+def test_decode_split_k_reduction_paths(cluster):
+    """Both split-K reductions of the decode kernel -- L2 atomics + last-contributor finalise (0) and the cluster /
+    distributed-shared-memory reduce (1) -- integer-exact for 2 / 4 / 8-way splits (tests/gemm_splitk_worker.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OB_GEMM_DEC_CLUSTER=cluster)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "gemm_splitk_worker.py")], capture_output=True, text=True,
+                       timeout=300, env=env, cwd=root)
+    assert r.returncode == 0 and "OK" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
 @pytest.mark.parametrize("N,K", [(1280, 8192), (8192, 1024), (7168, 8192), (8192, 3584)])
 def test_llama3_70b_tp8_shapes(N, K):
     """BASELINE config 4 (TP=8 shards, bs=16)."""

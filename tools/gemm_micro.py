@@ -127,6 +127,21 @@ if __name__ == "__main__" and os.environ.get("OB_DEC_EXP"):
     chain(64, TP8, 3, 0, tag="tp8 shard chain v2 auto")
     sys.exit(0)
 
+if __name__ == "__main__" and os.environ.get("OB_CL_EXP"):
+    # split-K reduction path A/B: run once with OB_GEMM_DEC_CLUSTER=0 (L2 reds + last-CTA finalise) and once with =1
+    # (cluster, distributed shared memory); -> profiles/r2_cluster_splitk.log
+    print("OB_GEMM_DEC_CLUSTER =", os.environ.get("OB_GEMM_DEC_CLUSTER"))
+    LL = [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)]
+    for M in (64, 16):
+        for (N, K), nm in zip(LL, ["qkv", "o_proj", "gate_up", "down"]):
+            run(M, N, K, mode=3, ctas=0, tag=f"{nm} v2 auto")
+    chain(64, LL, 3, 0, tag="layer chain v2 auto")
+    chain(16, LL, 3, 0, tag="layer chain v2 auto")
+    chain(64, [(768, 4096), (4096, 512), (3584, 4096), (4096, 1792)], 3, 0, tag="tp8 shard chain v2 auto")
+    chain(64, [(3072, 4096), (4096, 2048), (14336, 4096), (4096, 7168)], 3, 0, tag="tp2 shard chain v2 auto")
+    chain(16, [(10240, 8192), (8192, 8192), (57344, 8192), (8192, 28672)], 3, 0, layers=2, tag="70B layer chain (bs 16)")
+    sys.exit(0)
+
 if __name__ == "__main__" and os.environ.get("OB_2CTA_SWEEP"):
     for two in ("0", "1"):
         os.environ["OB_GEMM_2CTA"] = two
