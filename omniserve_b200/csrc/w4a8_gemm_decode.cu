@@ -9,9 +9,12 @@
 //   * the CTA is small -- <= 99 KB shared memory, 256 tensor-memory columns, <= 80 registers x 384 threads -- so two
 //     CTAs fit on an SM: two CTAs of this GEMM (independent pipelines) or this GEMM's CTA next to the CTA of the next
 //     kernel of the decode chain, which programmatic dependent launch lets in early to prefetch ITS weights;
-//   * no shared-memory staging in the epilogue: split tiles are accumulated with red.global.add.s32 straight from the
-//     TMEM registers (128-byte coalesced, exact, order independent) and finished by the last contributor, full tiles are
-//     stored as fp16 directly; the unpack warps run the epilogue themselves (a decode CTA has 1-3 segments).
+//   * split tiles: the K-slices of a tile are the CTAs of one cluster; each parks its INT32 partial in its own shared
+//     memory, one barrier.cluster, every CTA sums ITS token columns from all peers over distributed shared memory and
+//     stores fp16 -- exact, no L2 atomics, no "last CTA" (round 2: the L2 path below cost 4-6 us of dependent round trips per
+//     GEMM).  Splits that are not an aligned 2/4/8-way split fall back to red.global.add.s32 straight from the TMEM
+//     registers + arrival counter + finalisation by the last contributor.  Full tiles are stored as fp16 directly; the unpack
+//     warps run the epilogue themselves (a decode CTA has 1-3 segments).
 //
 // Replaces the same reference kernels as w4a8_gemm.cu (per_chn/gemm_cuda.cu:308-657, per_group/gemm_cuda.cu:333-707).
 #include "launch.h"
@@ -40,7 +43,7 @@ constexpr int ACC_COLS = 64;
 #endif
 constexpr int KPS = OB_DEC_KPS;
 #ifndef OB_DEC_CLUSTER_DEFAULT
-#define OB_DEC_CLUSTER_DEFAULT false
+#define OB_DEC_CLUSTER_DEFAULT true    // split-K inside a cluster over DSMEM (profiles/r2_cluster_splitk.log: 49.3 -> 43.7 us / layer)
 #endif
 constexpr int AB_STAGES = (TMEM_COLS - ACC_COLS) / (A_COLS * KPS);   // 3 steps: TMEM A ring == activation ring depth
 
@@ -563,9 +566,9 @@ static bool cluster_ok(int dev, int s) {
 // choice on B200 (profiles/r2_upc_sweep.log; the ~3.5 us launch floor is common to all and left out):
 //   * an SM moves one K-block per ~0.2 us however many CTAs share it: streaming = (CTAs per SM) x upc x 0.2;
 //   * a tile that is not split ends with a ~0.3 us epilogue (direct fp16 stores);
-//   * ANY split costs ~5 us (reds, fence, arrival counter, read-back and finalisation by the last contributor), plus
-//     ~0.01 us per contributing CTA of L2 atomic traffic -- so a whole 32-K-block tile per CTA (6.4 us) beats an 8-way
-//     split of it, and splitting only pays for long K (down_proj) or very few tiles;
+//   * a split through L2 costs ~5 us (reds, fence, arrival counter, read-back and finalisation by the last contributor:
+//     four dependent L2 round trips), plus ~0.01 us per contributing CTA of atomic traffic; an aligned 2 / 4 / 8-way split
+//     whose K-slices form one cluster is reduced over distributed shared memory instead and costs ~1.5 us;
 //   * ranges that straddle tile boundaries add a second epilogue and an uneven finish (~3 us).
 static bool cluster_split(int KB, int upc) {   // an aligned 2 / 4 / 8-way split: the K-slices of a tile form one cluster
   if (upc >= KB || KB % upc) return false;

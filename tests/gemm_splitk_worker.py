@@ -26,16 +26,16 @@ def case(M, N, K, ctas, per_group, seed):
     s1 = np.ones(N, np.float16)
     sa = np.ones(M, np.float16)
     out = torch.full((M, N), float("nan"), dtype=torch.float16, device="cuda")
+    ta, tq, ts1, tsa = t(a), t(qw), t(s1), t(sa)     # keep every device tensor alive until the launch has finished
     if per_group:
         ng = K // 128
-        s2 = ow.pack_s2(np.ones((N, ng), np.int64)).astype(np.int8)
-        z2 = ow.pack_s2(np.zeros((N, ng), np.int64)).astype(np.int8)
-        code = L.lib().ob_w4a8_gemm_ex(1, L.ptr(t(a)), L.ptr(t(qw)), L.ptr(t(z2)), L.ptr(t(s2)), L.ptr(t(s1)), L.ptr(t(sa)), 0, 0,
+        ts2 = t(ow.pack_s2(np.ones((N, ng), np.int64)).astype(np.int8))
+        tz2 = t(ow.pack_s2(np.zeros((N, ng), np.int64)).astype(np.int8))
+        code = L.lib().ob_w4a8_gemm_ex(1, L.ptr(ta), L.ptr(tq), L.ptr(tz2), L.ptr(ts2), L.ptr(ts1), L.ptr(tsa), 0, 0,
                                        L.ptr(out), M, N, K, N, 0, 3, ctas, L.stream())
     else:
-        szs = np.zeros(N, np.float16)
-        ssum = np.zeros(M, np.float16)
-        code = L.lib().ob_w4a8_gemm_ex(0, L.ptr(t(a)), L.ptr(t(qw)), 0, 0, L.ptr(t(s1)), L.ptr(t(sa)), L.ptr(t(szs)), L.ptr(t(ssum)),
+        tszs, tssum = t(np.zeros(N, np.float16)), t(np.zeros(M, np.float16))
+        code = L.lib().ob_w4a8_gemm_ex(0, L.ptr(ta), L.ptr(tq), 0, 0, L.ptr(ts1), L.ptr(tsa), L.ptr(tszs), L.ptr(tssum),
                                        L.ptr(out), M, N, K, N, 0, 3, ctas, L.stream())
     torch.cuda.synchronize()
     assert code == 0, code
