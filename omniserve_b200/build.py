@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+LIBDIR = os.path.join(HERE, os.environ.get("OB_BUILD_LIBDIR", "lib"))     # e.g. lib_timing for an instrumented variant (OB_LIB_PATH)
 LIB = os.path.join(LIBDIR, "libomniserve_b200.so")
 SOURCES = ["w4a8_gemm.cu", "w4a8_gemm_decode.cu", "w8a8_gemm.cu", "small_ops.cu", "kv4_attention.cu", "lserve_ops.cu", "c_api.cu"]
 NVCC_FLAGS = [
@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "--compiler-options", "-fPIC", "-Xptxas", "-v",
 ] + (["-DOB_GEMM_TIMING"] if os.environ.get("OB_GEMM_TIMING") == "1" else []) + (
     ["-DOB_DEC_TIMING"] if os.environ.get("OB_DEC_TIMING") == "1" else []) + (
+    ["-DOB_ATT_TIMING"] if os.environ.get("OB_ATT_TIMING") == "1" else []) + (
     [f"-DOB_DEC_KPS={os.environ['OB_DEC_KPS']}"] if os.environ.get("OB_DEC_KPS") else []) + (
     ["-DOB_DEC_WAIT_FIRST"] if os.environ.get("OB_DEC_WAIT_FIRST") == "1" else [])  # per-role wait counters (tools/gemm_waits.py)
 

@@ -130,7 +130,24 @@ struct AttnParams {
   int stable_history;
   // per-tensor KV8 cache (fused_attention_per_tensor_*): device float[2] = (K, V) dequant / quant scales; null = KV4
   const float* kv_scale_quant_orig; const float* kv_scale_orig_quant;
+  long long* dbg_t;   // -DOB_ATT_TIMING builds only (tools/att_timeline.py): [CTA][16] globaltimer stamps
+  int dbg_mode;       // -DOB_ATT_TIMING builds only, RESULTS INVALID: 1 = consumers skip the math, 2 = no scale / zero row copies
 };
+
+#ifdef OB_ATT_TIMING
+OB_DEVICE long long att_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define OB_AT(slot)                                                                                                        \
+  do {                                                                                                                     \
+    if (p.dbg_t) p.dbg_t[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = att_gtime(); \
+  } while (0)
+#else
+#define OB_AT(slot) (void)0
+#endif
+#ifdef OB_ATT_TIMING
+#define OB_ATT_MODE(bit) ((p.dbg_mode & (bit)) != 0)
+#else
+#define OB_ATT_MODE(bit) false
+#endif
 
 // invoke_quant(_fuse_sum) (fused_kernels.cu:57-142) of one attention-output row by the first 128 threads of the CTA,
 // with the element-to-thread assignment and reduction order of small_ops.cu:quant_kernel (bit-identical results).
@@ -219,6 +236,9 @@ OB_DEVICE void fused_quant_tail(const AttnParams& p, int b, int* flag, float* re
 //     (LDS.64) fragment loads are at most 2-way bank conflicted.
 //   * the four warps (and, for the split that owns it, the new token) are merged like KV splits.
 // ------------------------------------------------------------------------------------------------
+#ifndef OB_ATT_PAIR
+#define OB_ATT_PAIR 1       // KV4 page loop: two pages per round (0 = the one-page loop, kept for A/B and used by KV8)
+#endif
 constexpr int V2_STAGES = 4;
 constexpr int V2_STAGE_BYTES = 2 * 4096 + 4 * 128;
 // per-tensor KV8 pages (fused_attention_per_tensor_*, cache_engine.py:73-88): a (page, head) slice is 64 tokens x 128 int8 of
@@ -304,6 +324,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
   __shared__ float red_s[64];
 
   pdl_trigger();
+  if (threadIdx.x == 0) OB_AT(0);      // entry
   if (!p.stable_history) pdl_wait();   // e.g. a decode launched straight after the prefill writer of the same pages
   const int split = blockIdx.x;
   const int b = blockIdx.z;
@@ -383,10 +404,12 @@ kv4_decode_kernel(const AttnParams p, const int G) {
           const uint8_t* kp = reinterpret_cast<const uint8_t*>(kptr_s[i]);
           const uint8_t* vp = reinterpret_cast<const uint8_t*>(vptr_s[i]);
           uint8_t* st = ring + s * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          if (vb + i == v0) OB_AT(8);           // producer: first page issued
+          if (vb + i == v1 - 1) OB_AT(9);       // producer: last page issued
+          mbar_arrive_expect_tx(&full[s], OB_ATT_MODE(2) ? 2 * SLICE : STAGE_BYTES);
           bulk_g2s(st, kp + (size_t)sv.rank * SLICE, SLICE, &full[s]);
           bulk_g2s(st + SLICE, vp + (size_t)sv.rank * SLICE, SLICE, &full[s]);
-          if (!KV8) {
+          if (!KV8 && !OB_ATT_MODE(2)) {
             bulk_g2s(st + 8192, kp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
             bulk_g2s(st + 8192 + 128, kp + sv.data_bytes + (sv.hpool + sv.rank) * 128, 128, &full[s]);
             bulk_g2s(st + 8192 + 256, vp + sv.data_bytes + sv.rank * 128, 128, &full[s]);
@@ -408,7 +431,9 @@ kv4_decode_kernel(const AttnParams p, const int G) {
         sincosf(inv_freq, &rope_sn[tid], &rope_cs[tid]);
       }
     }
+    if (tid == 0) OB_AT(1);   // pre-dependency prologue done (tables, RoPE angles)
     pdl_wait();  // q, k, v are the previous kernel's output
+    if (tid == 0) OB_AT(2);   // grid dependency resolved
     asm volatile("bar.sync 1, 128;" ::: "memory");
     {
       const int half_rot = p.rotary_dim >> 1;
@@ -511,6 +536,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
     // ================================================================ compute warps
+    if (tid == 0) OB_AT(3);   // q / k RoPE, new-token logit, append done: page loop starts
     const int g = lane >> 2, c = lane & 3;
     uint32_t qB[16];
     if (KV8) {
@@ -538,10 +564,128 @@ kv4_decode_kernel(const AttnParams p, const int G) {
     const uint32_t v_off0 = SLICE + (base + kappa(2 * c)) * ROW_BYTES + g * VCH, v_off1 = SLICE + (base + kappa(2 * c + 1)) * ROW_BYTES + g * VCH;
     const uint32_t v_off2 = SLICE + (base + kappa(8 + 2 * c)) * ROW_BYTES + g * VCH, v_off3 = SLICE + (base + kappa(9 + 2 * c)) * ROW_BYTES + g * VCH;
     int s = 0, ph = 0;
+#if OB_ATT_PAIR
+    if constexpr (!KV8) {
+      // ---------------------------------------------------------------------------------------------------------------
+      // KV4 page loop, TWO pages per round.  The page loop is bound by the math of the four compute warps, not by the loads
+      // (profiles/r2_att_timeline.log: with the math switched off the same loop streams at 6.8 TB/s, with it 3.2 TB/s; ~8
+      // stall cycles per issued instruction with 3.5 warps per scheduler).  Two pages per round give every warp two
+      // independent K chains, one max / rescale / branch sequence per 32 tokens instead of 16, and two MMAs per accumulator
+      // in the V phase; shared-memory and barrier addresses are 32-bit values formed once, masks are selects.
+      // An odd tail page runs as a pair whose second half is masked (its stage pointer aliases the first).
+      // ---------------------------------------------------------------------------------------------------------------
+      const uint32_t ring_u32 = smem_u32(ring), full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
+      auto k_phase = [&](uint32_t st, float (&sa)[4], float (&sb)[4]) {
+        const uint4 ka = lds_v4(st + ka_off), kb = lds_v4(st + kb_off);
+        const uint32_t kaw[4] = {ka.x, ka.y, ka.z, ka.w}, kbw[4] = {kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+          const uint32_t ta = kaw[w] >> 8, tb = kbw[w] >> 8;
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(a0) : "r"(kaw[w]));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(a1) : "r"(kaw[w]));
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(a2) : "r"(ta));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(a3) : "r"(ta));
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(b0) : "r"(kbw[w]));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(b1) : "r"(kbw[w]));
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(b2) : "r"(tb));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(b3) : "r"(tb));
+          mma16816(sa, a0, b0, a1, b1, qB[4 * w], qB[4 * w + 1]);
+          mma16816(sb, a2, b2, a3, b3, qB[4 * w + 2], qB[4 * w + 3]);
+        }
+      };
+      // log2-domain logits of this lane's two tokens (a, b) x two heads (2c, 2c+1) of one page; masked tokens -> -inf
+      auto logits = [&](uint32_t st, const float (&sa)[4], const float (&sb)[4], bool va, bool vb, float (&lg)[4]) {
+        const float ksa = lds_f16(st + 8192 + 2 * tok_a), kza = lds_f16(st + 8192 + 128 + 2 * tok_a);
+        const float ksb = lds_f16(st + 8192 + 2 * tok_b), kzb = lds_f16(st + 8192 + 128 + 2 * tok_b);
+        const float a0 = ksa * ((sa[0] + sb[0]) - qb0 - kza * qs0) * qk_scale, a1 = ksa * ((sa[1] + sb[1]) - qb1 - kza * qs1) * qk_scale;
+        const float b0 = ksb * ((sa[2] + sb[2]) - qb0 - kzb * qs0) * qk_scale, b1 = ksb * ((sa[3] + sb[3]) - qb1 - kzb * qs1) * qk_scale;
+        lg[0] = va ? a0 : -INFINITY; lg[1] = va ? a1 : -INFINITY;
+        lg[2] = vb ? b0 : -INFINITY; lg[3] = vb ? b1 : -INFINITY;
+      };
+      // probabilities of one page -> P'^T B fragments (scaled by the V scale), softmax sums and zero-point corrections
+      auto probs = [&](uint32_t st, const float (&lg)[4], bool va, bool vb, uint32_t& pb_lo, uint32_t& pb_hi) {
+        const float pa0 = ex2(lg[0] - m0), pa1 = ex2(lg[1] - m1), pb0 = ex2(lg[2] - m0), pb1 = ex2(lg[3] - m1);
+        l0 += pa0 + pb0;
+        l1 += pa1 + pb1;
+        const float vsa_ = lds_f16(st + 8192 + 256 + 2 * tok_a), vza_ = lds_f16(st + 8192 + 384 + 2 * tok_a);
+        const float vsb_ = lds_f16(st + 8192 + 256 + 2 * tok_b), vzb_ = lds_f16(st + 8192 + 384 + 2 * tok_b);
+        const float vsa = va ? vsa_ : 0.f, vza = va ? vza_ : 0.f, vsb = vb ? vsb_ : 0.f, vzb = vb ? vzb_ : 0.f;
+        const __half2 ha = __floats2half2_rn(pa0 * vsa, pa1 * vsa), hb = __floats2half2_rn(pb0 * vsb, pb1 * vsb);
+        const float2 fa = __half22float2(ha), fb = __half22float2(hb);  // the values the MMA will really use
+        sp0 += fa.x + fb.x;
+        sp1 += fa.y + fb.y;
+        corr0 += fa.x * vza + fb.x * vzb;
+        corr1 += fa.y * vza + fb.y * vzb;
+        pb_lo = movmatrix_trans(h2_as_u32(ha));
+        pb_hi = movmatrix_trans(h2_as_u32(hb));
+      };
+      auto v_phase = [&](uint32_t st, uint32_t pb_lo, uint32_t pb_hi) {
+        const uint2 w0 = lds_v2(st + v_off0), w1 = lds_v2(st + v_off1), w2 = lds_v2(st + v_off2), w3 = lds_v2(st + v_off3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t A = j < 4 ? w0.x : w0.y, B = j < 4 ? w1.x : w1.y, Cw = j < 4 ? w2.x : w2.y, D = j < 4 ? w3.x : w3.y;
+          const uint32_t sel = (uint32_t)(j & 3) | ((uint32_t)(4 + (j & 3)) << 8);
+          const uint32_t u01 = __byte_perm(A, B, sel), u23 = __byte_perm(Cw, D, sel);
+          uint32_t t0, t1, t2, t3;
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(t0) : "r"(u01));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(t1) : "r"(u01));
+          asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(t2) : "r"(u23));
+          asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(t3) : "r"(u23));
+          mma16816(acc[j], t0, t1, t2, t3, pb_lo, pb_hi);
+        }
+      };
+      for (int v = v0; v < v1; v += 2) {
+        const bool two = v + 1 < v1;
+        const Visit x0 = vis.get(v);
+        const Visit x1 = two ? vis.get(v + 1) : x0;
+        const int s1 = two ? (s + 1 == NSTAGE ? 0 : s + 1) : s;
+        const int ph1 = (two && s + 1 == NSTAGE) ? ph ^ 1 : ph;
+        mbar_wait_a(full_u32 + s * 8, ph);
+        if (two) mbar_wait_a(full_u32 + s1 * 8, ph1);
+        const uint32_t st0 = ring_u32 + s * STAGE_BYTES, st1 = ring_u32 + s1 * STAGE_BYTES;
+        float sa0[4] = {0.f, 0.f, 0.f, 0.f}, sb0[4] = {0.f, 0.f, 0.f, 0.f}, sa1[4] = {0.f, 0.f, 0.f, 0.f}, sb1[4] = {0.f, 0.f, 0.f, 0.f};
+        k_phase(st0, sa0, sb0);
+        k_phase(st1, sa1, sb1);
+        const bool va0 = tok_a >= x0.lo && tok_a < x0.hi, vb0 = tok_b >= x0.lo && tok_b < x0.hi;
+        const bool va1 = two && tok_a >= x1.lo && tok_a < x1.hi, vb1 = two && tok_b >= x1.lo && tok_b < x1.hi;
+        float lg0[4], lg1[4];
+        logits(st0, sa0, sb0, va0, vb0, lg0);
+        logits(st1, sa1, sb1, va1, vb1, lg1);
+        // ---------------- online softmax over the 32 tokens (lanes with equal c share the heads 2c, 2c+1)
+        float x0m = fmaxf(fmaxf(lg0[0], lg0[2]), fmaxf(lg1[0], lg1[2])), x1m = fmaxf(fmaxf(lg0[1], lg0[3]), fmaxf(lg1[1], lg1[3]));
+#pragma unroll
+        for (int k = 4; k <= 16; k <<= 1) {
+          x0m = fmaxf(x0m, __shfl_xor_sync(0xffffffffu, x0m, k));
+          x1m = fmaxf(x1m, __shfl_xor_sync(0xffffffffu, x1m, k));
+        }
+        const float n0 = fmaxf(m0, x0m), n1 = fmaxf(m1, x1m);
+        if (__any_sync(0xffffffffu, n0 != m0 || n1 != m1)) {
+          const float f0 = ex2(m0 - n0), f1 = ex2(m1 - n1);
+          l0 *= f0; l1 *= f1; corr0 *= f0; corr1 *= f1; sp0 *= f0; sp1 *= f1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[j][0] *= f0; acc[j][1] *= f1; acc[j][2] *= f0; acc[j][3] *= f1; }
+          m0 = n0; m1 = n1;
+        }
+        uint32_t p0_lo, p0_hi, p1_lo, p1_hi;
+        probs(st0, lg0, va0, vb0, p0_lo, p0_hi);
+        probs(st1, lg1, va1, vb1, p1_lo, p1_hi);
+        v_phase(st0, p0_lo, p0_hi);
+        v_phase(st1, p1_lo, p1_hi);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_a(empty_u32 + s * 8);
+          if (two) mbar_arrive_a(empty_u32 + s1 * 8);
+        }
+        if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        if (two && ++s == NSTAGE) { s = 0; ph ^= 1; }
+      }
+    } else
+#endif
     for (int v = v0; v < v1; ++v) {
       const Visit vv = vis.get(v);
       mbar_wait(&full[s], ph);
-      if (base < vv.hi && base + 16 > vv.lo) {
+      if (base < vv.hi && base + 16 > vv.lo && !OB_ATT_MODE(1)) {
         const uint8_t* st = ring + s * STAGE_BYTES;
         const __half* ksc = reinterpret_cast<const __half*>(st + 8192);
         float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -676,6 +820,7 @@ kv4_decode_kernel(const AttnParams p, const int G) {
       if (lane == 0) mbar_arrive(&empty[s]);
       if (++s == NSTAGE) { s = 0; ph ^= 1; }
     }
+    if (tid == 0) OB_AT(4);   // page loop done (warp 0)
     // per-warp totals: l, sp and corr are per-thread partials over the rows g of equal c
 #pragma unroll
     for (int k = 4; k <= 16; k <<= 1) {
@@ -737,7 +882,9 @@ kv4_decode_kernel(const AttnParams p, const int G) {
     }
   }
   if (p.n_split == 1) {
+    if (tid == 0) OB_AT(5);   // outputs of this CTA stored
     if (p.q_out) fused_quant_tail(p, b, &flag_s, red_s);
+    if (tid == 0) OB_AT(6);   // exit (the last CTA of a sequence: after the fused row quantisation)
     return;
   }
   __threadfence();
@@ -1097,6 +1244,14 @@ int kv4_decode_run(const KV4DecodeArgs& a, cudaStream_t st) {
   p.sub_chunk = a.tokens_per_sub_chunk; p.eles_per_ind = a.hidden_dim_per_retrieval_token;
   p.q_out = a.q_out; p.q_scale = a.q_scale; p.q_sum = a.q_sum; p.tok_counters = nullptr;
   p.stable_history = a.stable_history;
+#ifdef OB_ATT_TIMING
+  {
+    const char* e = getenv("OB_ATT_DBGT");
+    p.dbg_t = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr;
+    const char* m = getenv("OB_ATT_DBG");      // read at every launch: the tool switches modes between graphs
+    p.dbg_mode = m ? atoi(m) : 0;
+  }
+#endif
   if (p.q_out) {
     if (!p.q_scale || (a.Hq * DH) % 8 || (a.Hq * DH) / 8 > 8 * 128 || a.B > 32768) return OB_ERR_SHAPE;
     if (int e = get_att_ws(dev, st, &ws)) return e;

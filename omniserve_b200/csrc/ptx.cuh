@@ -64,6 +64,22 @@ OB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// the same with 32-bit shared-window addresses computed once by the caller (a generic pointer is converted at every use)
+OB_DEVICE void mbar_wait_a(uint32_t bar_u32, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_u32), "r"(parity)
+        : "memory");
+  }
+}
+OB_DEVICE void mbar_arrive_a(uint32_t bar_u32) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_u32) : "memory");
+}
 // cluster-scope variants for barriers that CTAs of the same cluster arrive on remotely
 OB_DEVICE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -300,6 +316,16 @@ OB_DEVICE uint4 lds_v4(uint32_t saddr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
   return v;
+}
+OB_DEVICE uint2 lds_v2(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+  return v;
+}
+OB_DEVICE float lds_f16(uint32_t saddr) {     // one fp16 value, widened
+  unsigned short h;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(saddr));
+  return __half2float(__ushort_as_half(h));
 }
 OB_DEVICE uint32_t lds_u32(uint32_t saddr) {
   uint32_t v;

@@ -49,9 +49,11 @@ def main():
     n = 0
     for per_group in (False, True):
         for M in (7, 16, 32, 64):
-            for N, K, tiles in ((256, 1024, 2), (384, 2048, 3)):
+            for N, K, tiles in ((256, 1024, 2), (384, 2048, 3), (256, 1792, 2)):
                 kb = K // 128
                 for s in (2, 4, 8):
+                    if kb % s:
+                        continue                              # K = 1792: 14 K-blocks -> only the 2-way split (7 per CTA: odd tail step)
                     for rep in range(2):                      # twice: the L2 path must leave its workspace clean
                         case(M, N, K, tiles * s, per_group, seed=1000 * M + s + rep)
                         n += 1

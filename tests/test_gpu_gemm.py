@@ -54,6 +54,16 @@ def test_llama3_8b_decode_shapes_bs64(N, K):
     assert run(64, N, K, False, seed=N + K) > 0.999
 
 
+@pytest.mark.parametrize("tp", [2, 4, 8])
+def test_llama3_8b_tensor_parallel_shard_shapes_bs64(tp):
+    """The per-GPU GEMM shapes of Llama-3-8B under TP = 2 / 4 / 8 at M = 64 (column shards of qkv / gate_up, row shards of
+    o_proj / down_proj): short K (4 .. 56 K-blocks) and few tiles, i.e. the scheduler's cluster split-K choices incl. odd
+    K-block counts per CTA."""
+    for N, K in ((6144 // tp, 4096), (4096, 4096 // tp), (28672 // tp, 4096), (4096, 14336 // tp)):
+        assert run(64, N, K, False, seed=N + K + tp) > 0.999
+    assert run(64, 4096, 14336 // tp, True, seed=tp) > 0.999
+
+
 @pytest.mark.parametrize("cluster", ["0", "1"])
 def test_decode_split_k_reduction_paths(cluster):
     """Both split-K reductions of the decode kernel -- L2 atomics + last-contributor finalise (0) and the cluster /
