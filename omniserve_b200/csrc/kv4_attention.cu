@@ -8,17 +8,21 @@
 //
 // Design differences from the reference (which launches one CTA per *query* head and keeps every
 // logit of the context in shared memory):
-//   * one CTA per (sequence, KV head, KV split) serves the whole GQA group, so K/V nibbles are read
+//   * one CTA per (sequence, KV head, KV split) serves the whole GQA group, so K/V bytes are read
 //     from HBM once per KV head instead of once per query head;
-//   * 16-byte coalesced loads (4 lanes x 16 B per token row for K, 8 lanes x 8 B for V);
-//   * the per-token scale/zero are folded out of the inner loops:
-//       q.k = s*(sum_d q_d (n_d-8)) + s*(8-z)*sum_d q_d ;  sum_t p_t v_t = sum_t (p_t s_t)(n-8) - sum_t p_t s_t (z_t-8)
-//     so the loops work on exact small integers in half2 and never touch a dequant FMA;
-//   * P.V accumulates in half2 for 8 tokens and is flushed to fp32 (reference: fp32 throughout);
-//   * split-KV with (max,sum,out) partials merged by the last-arriving CTA (flash-decoding), so the
-//     context length is not bounded by shared memory.
-// Numerics therefore agree with the reference to ~1e-3 (north-star tolerance), not bit-exactly; the KV
-// page bytes written for the new token follow the reference formula exactly.
+//   * a producer warp streams each visited (page, head) slice -- 4 KB K + 4 KB V (+ 4 x 128 B of per-token
+//     scales / zeros for KV4) -- into a shared-memory ring with cp.async.bulk + mbarrier; four compute warps run
+//     flash-decoding on 16 tokens of the page each with mma.sync.m16n8k16;
+//   * the per-token scale/zero are folded out of the MMAs: nibbles enter as the exact fp16 numbers 1024 + n
+//     (even dims) and 1024 + 16 n (odd dims; q is pre-divided by 16 there), one lop3 per pair,
+//       q.k   = s_t * (S - 1024 * sum_d q'_d - z_t * sum_d q_d)
+//       P.V_d = sum_t (p_t s_t) (1024 + c n) / c  -  1024 * sum_t p_t s_t  -  sum_t p_t s_t z_t
+//     so the inner loops never touch a dequant FMA (INT8 pages: 1152 + code, one prmt per pair, per-tensor scales);
+//   * split-KV with (max, sum, out) partials merged by the last-arriving CTA (flash-decoding), so the context
+//     length is not bounded by shared memory; optional fused per-token INT8 quantisation of the output row.
+// Numerics agree with the reference to ~1e-3 of the output scale (north-star tolerance; measured closer to exact
+// arithmetic than the reference kernels, tests/test_gpu_parity_r2.py), not bit-exactly; the KV page bytes written for
+// the new token follow the reference formula exactly.
 #include "kv4_attention.h"
 #include "launch.h"
 #include "ptx.cuh"
@@ -31,8 +35,6 @@ namespace ob {
 
 constexpr int DH = 128;
 constexpr int TPB = 64;            // tokens per page
-constexpr int ATT_THREADS = 128;
-constexpr int MAX_CHUNK = 4096;    // cached tokens handled by one CTA (logits live in smem)
 
 struct SeqView {
   const int64_t* ktab;  // this sequence's K page pointers
@@ -44,34 +46,12 @@ struct SeqView {
   int rank;             // row of this kv head inside its pool's pages
   int data_bytes;       // H_pool * 64 * 64
   int hpool;
-  OB_DEVICE int pos_of(int i) const {
-    if (mode == 1) return i < sink_tok ? i : i + gap;
-    if (mode == 2) return dyn[i >> 6] * TPB + (i & 63);
-    return i;
-  }
   OB_DEVICE int tab_idx(int pos) const {
     int blk = pos >> 6;
     if (mode == 1) blk = blk < sink_blk ? blk : sink_blk + (blk - sink_blk) % local_blk;
     return blk;
   }
 };
-
-// (n-8) as half2 pairs (n_j, n_{j+4}), j = 0..3, of one 32-bit word of 8 nibbles.
-OB_DEVICE void nib8_to_h2(uint32_t w, __half2 (&o)[4]) {
-  uint32_t t0, t1, t2, t3;
-  const uint32_t top = w >> 8;
-  asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(t0) : "r"(w));
-  asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(t1) : "r"(w));
-  asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(t2) : "r"(top));
-  asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(t3) : "r"(top));
-  const __half2 c1032 = __halves2half2(__ushort_as_half(0x6408), __ushort_as_half(0x6408));
-  const __half2 c16th = __halves2half2(__ushort_as_half(0x2c00), __ushort_as_half(0x2c00));
-  const __half2 cm72 = __halves2half2(__ushort_as_half(0xd480), __ushort_as_half(0xd480));
-  o[0] = __hsub2(*reinterpret_cast<__half2*>(&t0), c1032);
-  o[1] = __hfma2(*reinterpret_cast<__half2*>(&t1), c16th, cm72);
-  o[2] = __hsub2(*reinterpret_cast<__half2*>(&t2), c1032);
-  o[3] = __hfma2(*reinterpret_cast<__half2*>(&t3), c16th, cm72);
-}
 
 // Per-token/per-head asymmetric 4-bit quant of 128 fp16 values held 4 per lane by one warp
 // (lane l owns elements 4l..4l+3).  Template.hpp:1063-1081 + Utils.h:1838-1852.
