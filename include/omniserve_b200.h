@@ -65,6 +65,11 @@ int ob_w4a8_gemm_ex(int per_group, const int8_t* in_feats, const int8_t* kernel,
                     const int8_t* scales_i8, const void* wscales, const void* ascales, const void* w_szs,
                     const void* a_ssums, void* out_feats, int M, int N, int K, int ldc, int force_bn,
                     int force_mode, int force_ctas, void* stream);
+/* Host-only (no CUDA call, usable without a GPU): the scheduling decision the decode kernel (M <= 64) takes for a shape on a
+ * device with `sms` SMs -- token tile BN, K-blocks of 128 per CTA, CTAs, and the cluster size of an aligned 2 / 4 / 8-way
+ * split-K (0 = whole tiles or the L2 reduction).  For tests and tooling. */
+int ob_debug_w4a8_decode_plan(int M, int N, int K, int sms, int ctas_per_sm, int use_cluster, int* bn, int* units_per_cta,
+                              int* grid, int* cluster_s);
 
 /* Extension (decode-sized M): the W4A8 GEMM followed, in the same launch, by the residual add + norm + per-token quant
  * that consumes its output in the reference's layer (llama_w4a8_unpad.py:425-431: `residual + o_proj(...)` ->

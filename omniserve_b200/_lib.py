@@ -81,6 +81,7 @@ _SIGS = {
     "ob_w4a8_moe_gemm": ([c_p] * 8 + [c_i] * 5 + [c_p], c_i),
     "ob_w8a8_gemm": ([c_p] * 5 + [c_i] * 4 + [c_p], c_i),
     "ob_w4a8_gemm_ex": ([c_i] + [c_p] * 9 + [c_i] * 7 + [c_p], c_i),
+    "ob_debug_w4a8_decode_plan": ([c_i] * 6 + [c_p] * 4, c_i),
     "ob_w4a8_gemm_add_norm_quant": ([c_i] + [c_p] * 9 + [c_i] * 4 + [c_p] * 6 + [c_f] + [c_p], c_i),
     "ob_invoke_quant": ([c_p] * 3 + [c_i] * 2 + [c_p], c_i),
     "ob_invoke_quant_fuse_sum": ([c_p] * 4 + [c_i] * 2 + [c_p], c_i),

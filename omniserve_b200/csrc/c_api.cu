@@ -72,6 +72,11 @@ int ob_w4a8_gemm_per_group(const int8_t* in_feats, const int8_t* kernel, const i
                          ldc, 0, -1, 0, stream);
 }
 
+int ob_debug_w4a8_decode_plan(int M, int N, int K, int sms, int ctas_per_sm, int use_cluster, int* bn, int* units_per_cta,
+                              int* grid, int* cluster_s) {
+  return w4a8_gemm_decode_plan(M, N, K, sms, ctas_per_sm, use_cluster, bn, units_per_cta, grid, cluster_s);
+}
+
 int ob_w4a8_moe_gemm(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales,
                      const void* w_szs, const void* a_ssums, void* out_feats, const int* problem_sizes_host, int num_experts,
                      int T, int N, int K, int ldc, void* stream) {

@@ -38,6 +38,8 @@ int w4a8_gemm_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st);
 // columns, <= 80 registers) for two CTAs per SM -- of the same GEMM, or of this GEMM and its PDL-launched successor.
 // force_ctas = grid override (0 = auto).  Returns OB_ERR_SHAPE for shapes it does not take (caller falls back).
 int w4a8_gemm_decode_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st);
+int w4a8_gemm_decode_plan(int M, int N, int K, int sms, int ctas_per_sm, int use_cluster, int* bn, int* units_per_cta, int* grid,
+                          int* cluster_s);
 
 // Grouped (mixture-of-experts) W4A8 per-channel GEMM (w4a8_gemm_decode.cu), see include/omniserve_b200.h.
 int w4a8_moe_gemm_run(const int8_t* x, const int8_t* qweight, const __half* wscales, const __half* ascales, const __half* w_szs,

@@ -656,6 +656,27 @@ int w4a8_gemm_decode_run(const W4A8GemmArgs& a, bool per_group, cudaStream_t st)
   }
 }
 
+// Host-only view of the scheduling decision above (no CUDA call; tests/test_host_logic.py): which token tile, how many
+// K-blocks per CTA, how many CTAs and -- if the split is an aligned 2 / 4 / 8-way split -- the cluster size the launch
+// would ask for (the run additionally checks that such clusters can be co-scheduled on the device).
+int w4a8_gemm_decode_plan(int M, int N, int K, int sms, int ctas_per_sm, int use_cluster, int* bn, int* units_per_cta, int* grid,
+                          int* cluster_s) {
+  using namespace dec;
+  if (M <= 0 || M > 64 || N % 32 != 0 || K % 128 != 0 || sms <= 0 || ctas_per_sm < 1 || ctas_per_sm > 2) return OB_ERR_SHAPE;
+  const int BN = M <= 16 ? 16 : M <= 32 ? 32 : 64;
+  const int n_tiles = (N + BM - 1) / BM, kb = K / BK;
+  const long long units = (long long)n_tiles * kb;
+  const int upc = choose_upc(n_tiles, kb, sms, ctas_per_sm, BN, use_cluster != 0);
+  const int g = (int)((units + upc - 1) / upc);
+  int cs = 0;
+  if (use_cluster && cluster_split(kb, upc) && g == n_tiles * (kb / upc)) cs = kb / upc;
+  if (bn) *bn = BN;
+  if (units_per_cta) *units_per_cta = upc;
+  if (grid) *grid = g;
+  if (cluster_s) *cluster_s = cs;
+  return 0;
+}
+
 // Grouped W4A8 per-channel GEMM for mixture-of-experts layers (interface of the reference's
 // unreleased op, w4a8_moe_linear.py:83-94: x [T, K] int8 with the token rows sorted by expert, qweight [E, N, K/2] in the
 // reference tile layout per expert, s1_scales / s1_szeros [E, N], per-token input_scales / input_sum [T], problem_sizes[e] =

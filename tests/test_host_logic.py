@@ -145,3 +145,39 @@ def test_extension_entry_points_are_declared_and_exported():
         assert name in L.EXPORTS and f"int {name}(" in hdr
     for name in L.EXPORTS:
         assert name + "(" in hdr, f"{name} is bound by ctypes but not declared in the public header"
+
+
+def test_decode_gemm_scheduler_host_logic():
+    """w4a8_gemm_decode.cu: choose_upc / cluster_split through the host-only C-ABI query (no GPU): whole tiles when a tile per CTA
+    fills the machine, aligned 2 / 4 / 8-way splits whose K-slices form one cluster otherwise, grid = tiles x split, never more
+    CTAs than two per SM; without the cluster reduction the 5 us L2 split is avoided where a whole tile per CTA is cheaper."""
+    import ctypes as C
+    from omniserve_b200 import _lib as L
+    lib = L.lib()
+
+    def plan(M, N, K, cluster=1, sms=148):
+        bn, upc, grid, cs = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rc = lib.ob_debug_w4a8_decode_plan(M, N, K, sms, 2, cluster, C.addressof(bn), C.addressof(upc), C.addressof(grid), C.addressof(cs))
+        assert rc == 0
+        return bn.value, upc.value, grid.value, cs.value
+    # Llama-3-8B decode layer at bs = 64 on 148 SMs (DESIGN.md 4.1)
+    assert plan(64, 6144, 4096) == (64, 8, 192, 4)          # qkv: 48 tiles x 32 K-blocks, 4-way cluster split
+    assert plan(64, 4096, 4096) == (64, 4, 256, 8)          # o_proj: 8-way
+    assert plan(64, 28672, 4096) == (64, 32, 224, 0)        # gate_up: one whole tile per CTA, no reduction
+    assert plan(64, 4096, 14336) == (64, 14, 256, 8)        # down_proj: 112 K-blocks, 8-way
+    assert plan(64, 4096, 1792) == (64, 7, 64, 2)           # TP8 down shard: 14 K-blocks -> 2-way, odd K-block count per CTA
+    assert plan(64, 6144, 4096, cluster=0) == (64, 32, 48, 0)   # L2 reduction: a split costs more than whole tiles here
+    assert plan(16, 4096, 4096)[0] == 16 and plan(17, 4096, 4096)[0] == 32 and plan(33, 4096, 4096)[0] == 64
+    for M in (1, 16, 32, 64):
+        for N in (256, 768, 4096, 6144, 28672, 57344):
+            for K in (512, 1792, 4096, 8192, 14336, 28672):
+                bn, upc, grid, cs = plan(M, N, K)
+                tiles, kb = (N + 127) // 128, K // 128
+                assert 1 <= upc and grid == -(-tiles * kb // upc)
+                assert grid <= 2 * 148 or upc % kb == 0     # more CTAs than slots only as whole tiles queued on the SMs
+                if cs:
+                    assert cs in (2, 4, 8) and kb % upc == 0 and kb // upc == cs and grid == tiles * cs
+                if upc >= kb:
+                    assert upc % kb == 0 and cs == 0          # whole tiles per CTA
+    assert lib.ob_debug_w4a8_decode_plan(65, 4096, 4096, 148, 2, 1, None, None, None, None) != 0    # M > 64 is not this kernel's
+    assert lib.ob_debug_w4a8_decode_plan(64, 4096, 4000, 148, 2, 1, None, None, None, None) != 0    # K % 128
